@@ -1,0 +1,214 @@
+/*
+ * mmumap.h -- C ABI of the B200-native UMAP engine (libmmumap_b200.so).
+ *
+ * This is the lower drop-in boundary: the host-side mirror of the reference's Python API
+ * (multimodal-umap_b200/impl/model.py, util.py) calls these entry points through ctypes.
+ * The reference (aletheiaaaaa/Multimodal-UMAP) has no native layer of its own; each entry
+ * point below replaces a group of torch calls in /root/reference/impl/model.py, cited per
+ * function as "ref: model.py:<lines>".
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no allocation crosses the ABI: the caller allocates, the kernels fill;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all calls are asynchronous on `stream` unless stated; none synchronises the device;
+ *   - return value 0 = ok, non-zero = error; mmu_last_error() returns the message
+ *     (thread-local, valid until the next failing call on the same thread);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     MMU_ERR_CUDA.
+ *   - indices are int32 on the device (the reference uses int64 COO; the host mirror
+ *     converts at the Python boundary), row offsets are int64, all reals are fp32.
+ */
+#ifndef MMUMAP_H_
+#define MMUMAP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMU_ABI_VERSION 1
+
+#define MMU_OK 0
+#define MMU_ERR_ARG 1      /* invalid argument (message says which) */
+#define MMU_ERR_CUDA 2     /* CUDA runtime / launch error */
+#define MMU_ERR_UNSUPPORTED 3
+
+#define MMU_MAX_K 64       /* neighbours per row supported by the per-row kernels */
+
+typedef void *mmu_stream_t;
+
+int mmu_abi_version(void);
+const char *mmu_last_error(void);
+/* Device properties the host uses to size persistent grids. Synchronous. */
+int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+
+/* ------------------------------------------------------------------------------------
+ * K1/K2/K3  exact kNN graph            ref: model.py:81-195 (candidate search + per-row
+ *           top-k), distance model.py:109,163, selection model.py:181-193,
+ *           self-exclusion model.py:88,166.
+ *
+ * Result rows are sorted by (dist, index) ascending; dist = sqrtf(sum_t fmaf(diff,diff,.))
+ * accumulated over t ascending (the canonical order of oracle/knn_oracle.c).
+ * Rows with fewer than k admissible points are padded with idx=-1, dist=+inf.
+ * ---------------------------------------------------------------------------------- */
+
+/* Exhaustive fp32 kNN on CUDA cores (exact by construction; also the fallback for rows the
+ * tensor-core path cannot certify).  query_ids (nullable): if given, only the n_query rows
+ * query[query_ids[t]] are processed and results are written to row query_ids[t].
+ * query_index_base / db_index_base are the global indices of query row 0 / db row 0
+ * (multi-GPU shards); out_idx holds GLOBAL db indices.  If exclude_self, the pair whose
+ * global indices coincide is skipped.  If merge_existing, out_idx/out_dist are read as the
+ * running top-k (streaming over db shards, K3 fused). */
+int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_ids,
+                      const float *db, int64_t n_db, int dim, int k, int exclude_self,
+                      int64_t query_index_base, int64_t db_index_base, int merge_existing,
+                      int32_t *out_idx, float *out_dist, mmu_stream_t stream);
+
+/* K3: merge two sorted per-row lists (e.g. from two db shards) into one sorted top-k. */
+int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_b,
+                  const float *dist_b, int64_t n_rows, int k, int32_t *out_idx, float *out_dist,
+                  mmu_stream_t stream);
+
+/* K1 tensor-core candidate generation (tcgen05 / TMEM / TMA), see mmu_knn_tc_* below. */
+
+/* Prepare operands for the tensor-core path: split fp32 rows into bf16 hi/lo parts laid
+ * out [rows_padded x dim_padded] (dim_padded multiple of 64, zero filled) and fp32 squared
+ * norms.  lo may be NULL (single-pass bf16). */
+int mmu_knn_tc_prepare(const float *x, int64_t n_rows, int dim, int64_t rows_padded, int dim_padded,
+                       void *hi_bf16, void *lo_bf16, float *sqnorm, mmu_stream_t stream);
+
+/* Bytes of scratch mmu_knn_tc_candidates needs. */
+size_t mmu_knn_tc_workspace_bytes(int64_t n_query_padded, int n_cand);
+
+/* K1: for every query row produce n_cand (<= 64) candidate db indices with the smallest
+ * approximate squared distance  |q|^2 + |y|^2 - 2 q.y  (q.y from bf16 tensor-core MMAs with
+ * fp32 accumulation in TMEM; passes = 1: hi.hi, passes = 3: hi.hi + hi.lo + lo.hi), and the
+ * n_cand-th smallest approximate value as `cand_bound` (a lower bound on the approximate
+ * distance of every non-candidate).  If merge_existing, cand_* hold the running state
+ * (streaming over db shards).  Operands come from mmu_knn_tc_prepare. */
+int mmu_knn_tc_candidates(const void *q_hi, const void *q_lo, const float *q_sqnorm,
+                          int64_t n_query, int64_t n_query_padded,
+                          const void *db_hi, const void *db_lo, const float *db_sqnorm,
+                          int64_t n_db, int64_t n_db_padded, int dim_padded, int passes,
+                          int n_cand, int exclude_self, int64_t query_index_base,
+                          int64_t db_index_base, int merge_existing,
+                          int32_t *cand_idx, float *cand_d2, void *workspace, size_t workspace_bytes,
+                          mmu_stream_t stream);
+
+/* K2: rescore candidates with the canonical fp32 distance, select the k best by
+ * (dist, index), and certify each row: row is certified iff every non-candidate is provably
+ * farther than the k-th selected neighbour, i.e. sqrtf(cand_bound - eps_row) > dist_k with
+ * eps_row = err_coef * (|q|^2 + max|y|^2).  uncertified_rows/n_uncertified (device) receive
+ * the rows that must be recomputed with mmu_knn_exact_f32.  db rows are addressed by GLOBAL
+ * index minus db_index_base. */
+int mmu_knn_rescore(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim,
+                    const int32_t *cand_idx, const float *cand_d2, int n_cand, int k,
+                    const float *q_sqnorm, float db_sqnorm_max, float err_coef,
+                    int64_t db_index_base, int32_t *out_idx, float *out_dist,
+                    int32_t *uncertified_rows, int32_t *n_uncertified, mmu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  rho / sigma / membership weights   ref: model.py:33-61 (get_sigmas), :197-209
+ * One warp per row.  rho = row minimum.  solver 0 = bisection (64 steps) of
+ * sum_j exp(-(d_j-rho)/sigma) = log2(k); solver 1 = the reference's Newton iteration
+ * (n_iter steps from sigma=1, closed-form derivative, clamp >= 1e-6) reproducing its
+ * results including its divergent rows.  Outputs the row's k entries re-ordered by column
+ * (the order .coalesce() gives, model.py:208): col_sorted / w_sorted [n_rows x k].
+ * sigma / rho may be NULL.
+ * ---------------------------------------------------------------------------------- */
+#define MMU_SIGMA_BISECT 0
+#define MMU_SIGMA_NEWTON 1
+int mmu_smooth_knn(const int32_t *idx, const float *dist, int64_t n_rows, int k, int solver,
+                   int n_iter, float *sigma, float *rho, int32_t *col_sorted, float *w_sorted,
+                   mmu_stream_t stream);
+/* invert-mode weights 1/(1 + a d^(2b))       ref: model.py:206 */
+int mmu_invert_weights(const int32_t *idx, const float *dist, int64_t n_rows, int k, float a,
+                       float b, int32_t *col_sorted, float *w_sorted, mmu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5  fuzzy union S = G + G^T - G*G^T     ref: model.py:271
+ * G is the fixed-degree graph from K4 (n x k, columns ascending per row).  G^T is built by
+ * a stable LSD radix sort on the column key; each row then merges its two sorted lists.
+ * Output is coalesced COO/CSR: out_rowptr [n+1], out_row/out_col/out_val with capacity
+ * 2*n*k entries, sorted by (row, col); values fl(fl(a+b)-fl(a*b)) on mutual edges.
+ * out_rowptr[n] is the nnz.
+ * ---------------------------------------------------------------------------------- */
+size_t mmu_union_workspace_bytes(int64_t n, int k);
+int mmu_fuzzy_union(const int32_t *col, const float *w, int64_t n, int k, void *workspace,
+                    size_t workspace_bytes, int64_t *out_rowptr, int32_t *out_row,
+                    int32_t *out_col, float *out_val, mmu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K6  transform / invert initialisation    ref: model.py:236-252 (embed_query)
+ * out[q] = sum_j (w_qj / max(sum_j w_qj, 1e-6)) * ref[col_qj]
+ * ---------------------------------------------------------------------------------- */
+int mmu_embed_query(const int32_t *col, const float *w, int64_t n_rows, int k, const float *ref,
+                    int dim, float *out, mmu_stream_t stream);
+/* CSR SpMM Y = A X (A n x n fp32 CSR, X n x m row-major), used by the spectral init
+ * ref: model.py:227,232 (sp.mm / lobpcg operator application) */
+int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                 const float *x, int m, float *y, mmu_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K7/K8/K9  layout optimiser               ref: model.py:396-481 (_train),
+ *           :312-334 (attractive / repulsive terms), :364-394 (InfoNCE), :403,:474-476 (Adam)
+ * ---------------------------------------------------------------------------------- */
+
+/* Per-run optimiser state kept on the device so that epochs can be replayed from a CUDA
+ * graph: 8 x uint32 words {epoch, step, step_size(f32), bc2_sqrt(f32), reserved...}. */
+#define MMU_OPT_STATE_WORDS 8
+int mmu_opt_state_init(uint32_t *state, mmu_stream_t stream);
+/* epoch += 1, step += 1, recompute Adam's step_size = lr/(1-beta1^step) and
+ * bc2_sqrt = sqrt(1-beta2^step) in double precision. */
+int mmu_opt_state_advance(uint32_t *state, float lr, float beta1, float beta2, mmu_stream_t stream);
+
+/* K7a (device sample stream): Bernoulli(w) keep per edge (ref: model.py:432) with a
+ * counter-based Philox4x32-10 stream keyed by (seed, state->epoch, edge position).  Writes the
+ * kept edge positions (any order) to kept_pos, their number to *kept_count and the number
+ * kept in each row-batch (ref: model.py:423-424, batch = row / batch_size) to batch_kept.
+ * kept_count and batch_kept are zeroed by this call. */
+int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
+                    uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
+                    int32_t *batch_kept, mmu_stream_t stream);
+
+/* K7b: forces of every kept edge and its num_rep negatives, accumulated with red.global.add
+ * into the gradient table(s).  Gradient of
+ *   mean_batches[ mean_kept log(1+a s^b) + mean_{kept*R} -log(a s^b/(1+a s^b)+1e-6) ],
+ *   s = max(|y_i-y_j|^2, 1e-6)                         (ref: model.py:312-334,439-453).
+ * head/grad_head: the table being optimised [n_head x dim]; tail: table the column indices
+ * and negatives address (same pointer as head in fit mode, the frozen fitted table in
+ * transform mode); grad_tail: NULL in transform mode (ref: model.py:399-401,416).
+ * neg: [n_kept x num_rep] host-generated negative ids (ref: model.py:444) or NULL to draw
+ * them on the device (Philox, uniform in [0, rep_count)).
+ * kept_count: device scalar (number of valid entries of kept_pos).
+ * loss (nullable): device float accumulating the modality's loss. */
+int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
+                    const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
+                    int n_batches, int batch_size, int num_rep, int64_t rep_count,
+                    const float *head, const float *tail, float *grad_head, float *grad_tail,
+                    int dim, float a, float b, uint64_t seed, const uint32_t *state, float *loss,
+                    mmu_stream_t stream);
+
+/* K8: InfoNCE gradient for one direction (anchors e0 -> positives/negatives e1).
+ * ref: model.py:364-394.  perm [num] (nullable = identity) and neg [num x n_neg] (nullable =
+ * device Philox) are the host draws of model.py:373,383 in anchor order; anchors are
+ * weighted weight/(chunk_len*n_chunks) with chunks of `chunk` anchors (model.py:369,392-394);
+ * `weight` carries alpha (model.py:467-472). */
+int mmu_infonce(const float *e0, const float *e1, int64_t num, int dim, const int32_t *perm,
+                const int32_t *neg, int n_neg, int chunk, float weight, float temperature,
+                float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                const uint32_t *state, float *loss, mmu_stream_t stream);
+
+/* K9: fused Adam update over a dense table (torch.optim.Adam single-tensor semantics,
+ * eps=1e-8 style denominator sqrt(v)/bc2_sqrt + eps), reading step_size / bc2_sqrt from
+ * `state`; zero_grad != 0 also clears g.            ref: model.py:403,474-476 */
+int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, float beta1, float beta2,
+                  float eps, const uint32_t *state, int zero_grad, mmu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMUMAP_H_ */

@@ -1,0 +1,504 @@
+// layout_sgd.cu -- K7 (edge sampling + attractive/repulsive forces), K8 (InfoNCE), K9 (Adam).
+//
+// ref: /root/reference/impl/model.py:396-481 (_train), :312-334 (force terms),
+//      :364-394 (_infonce_loss), :403,:474-476 (Adam).
+//
+// The reference builds an autograd graph per epoch and lets index_put_(accumulate=True) scatter
+// the gradient; here the closed-form gradient of the same loss is accumulated straight into a
+// dense gradient table with vector red.global.add (Hogwild-style: no ordering between edges),
+// and a fused Adam pass consumes and clears it.  Edges are COO (row, col, w) sorted by
+// (row, col) as .coalesce() leaves them; a kept edge list (positions into that COO) is either
+// uploaded from the host-replayed sample stream (parity mode) or produced on the device by
+// mmu_edge_sample (Philox4x32-10 counter stream, throughput mode).
+#include "common.cuh"
+
+namespace mmu {
+
+// ------------------------------------------------------------------ optimiser state
+__global__ void opt_state_init_kernel(OptState *s) {
+    s->epoch = 0; s->step = 0; s->step_size = 0.f; s->bc2_sqrt = 1.f;
+    for (int i = 0; i < 4; ++i) s->reserved[i] = 0;
+}
+__global__ void opt_state_advance_kernel(OptState *s, float lr, float beta1, float beta2) {
+    uint32_t step = s->step + 1;
+    s->step = step;
+    s->epoch = s->epoch + 1;
+    double bc1 = 1.0 - pow((double)beta1, (double)step);
+    double bc2 = 1.0 - pow((double)beta2, (double)step);
+    s->step_size = (float)((double)lr / bc1);
+    s->bc2_sqrt = (float)sqrt(bc2);
+}
+
+// ------------------------------------------------------------------ K7a: edge sampling
+// thread handles 4 consecutive edges (one Philox call -> 4 uniforms)
+__global__ void __launch_bounds__(256)
+edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w, int64_t nnz, int batch_size,
+                   uint64_t seed, const OptState *__restrict__ st, int32_t *__restrict__ kept_pos,
+                   int32_t *__restrict__ kept_count, int32_t *__restrict__ batch_kept) {
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int lane = threadIdx.x & 31;
+    const int64_t n4 = (nnz + 3) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // all lanes of a warp iterate the same number of times (warp-level collectives below)
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    for (int64_t wbase = first; wbase < n4; wbase += stride) {
+        int64_t q = wbase + lane;
+        int32_t pos[4];
+        int cnt = 0;
+        int32_t brow[4];
+        if (q < n4) {
+            Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), epoch, STREAM_KEEP, k0, k1);
+            uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int64_t e = q * 4 + i;
+                if (e < nnz && u01(rv[i]) < w[e]) {     // ref: model.py:432  rand < w
+                    pos[cnt] = (int32_t)e;
+                    brow[cnt] = row[e] / batch_size;
+                    ++cnt;
+                }
+            }
+        }
+        // warp compaction
+        int excl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, excl, o);
+            if (lane >= o) excl += t;
+        }
+        int total = __shfl_sync(0xffffffffu, excl, 31);
+        excl -= cnt;
+        int base = 0;
+        if (lane == 0 && total) base = atomicAdd(kept_count, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = 0; i < cnt; ++i) kept_pos[base + excl + i] = pos[i];
+        // per-batch counts, aggregated on the warp's most common batch (edges are row sorted)
+        unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
+        int src_lane = has ? __ffs(has) - 1 : 0;
+        int b_ref = __shfl_sync(0xffffffffu, cnt ? brow[0] : -1, src_lane);
+        int same = 0;
+        for (int i = 0; i < cnt; ++i) {
+            if (brow[i] == b_ref) ++same;
+            else atomicAdd(&batch_kept[brow[i]], 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
+        if (lane == 0 && same) atomicAdd(&batch_kept[b_ref], same);
+    }
+}
+
+// ------------------------------------------------------------------ K7b: forces
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int VEC>
+struct Vec {
+    float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> load_vec(const float *p) {
+    Vec<VEC> r;
+    if (VEC == 4) { float4 t = *reinterpret_cast<const float4 *>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else if (VEC == 2) { float2 t = *reinterpret_cast<const float2 *>(p); r.v[0] = t.x; r.v[1] = t.y; }
+    else { r.v[0] = *p; }
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void red_vec(float *p, const Vec<VEC> &g, float sign) {
+    if (VEC == 4) red_add_v4(p, sign * g.v[0], sign * g.v[1], sign * g.v[2], sign * g.v[3]);
+    else if (VEC == 2) red_add_v2(p, sign * g.v[0], sign * g.v[1]);
+    else red_add_f32(p, sign * g.v[0]);
+}
+
+// attractive: d/ds log(1+a s^b);  repulsive: d/ds -log(a s^b/(1+a s^b)+1e-6)   (x2 for ds/dy)
+__device__ __forceinline__ void attr_terms(float s_raw, float a, float b, float &coef, float &loss) {
+    float s = fmaxf(s_raw, 1e-6f);
+    float sb = powf(s, b);
+    loss = logf(1.0f + a * sb);
+    coef = (s_raw >= 1e-6f) ? (2.0f * a * b * sb / s) / (1.0f + a * sb) : 0.0f;
+}
+__device__ __forceinline__ void rep_terms(float s_raw, float a, float b, float &coef, float &loss) {
+    float s = fmaxf(s_raw, 1e-6f);
+    float sb = powf(s, b);
+    float q = a * sb;
+    float f = q / (1.0f + q) + 1e-6f;
+    loss = -logf(f);
+    coef = (s_raw >= 1e-6f) ? -(2.0f * a * b * sb / s) / (f * (1.0f + q) * (1.0f + q)) : 0.0f;
+}
+
+// One group of LANES threads per kept edge; each thread owns VEC consecutive components
+// (dim == LANES*VEC), or, in the generic kernel (VEC==0), a warp per edge with strided components.
+template <int VEC, int LANES>
+__global__ void __launch_bounds__(256)
+edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                   const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                   const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
+                   int batch_size, int num_rep, uint32_t rep_count, const float *__restrict__ head,
+                   const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
+                   int dim, float a, float b, uint64_t seed, const OptState *__restrict__ st,
+                   float *__restrict__ loss_out) {
+    const int n_kept = *kept_count;
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int gl = threadIdx.x % LANES;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+    const float inv_nb = 1.0f / (float)n_batches;
+    float loss_acc = 0.f;
+    // groups of the same warp must iterate together (shuffles): round the trip count per warp
+    const int64_t gpw = 32 / LANES;                                  // groups per warp
+    const int64_t wfirst = (gid / gpw) * gpw;
+    for (int64_t e0 = wfirst; e0 < n_kept; e0 += n_groups) {
+        const int64_t e = e0 + (gid - wfirst);
+        const bool active = e < n_kept;
+        int32_t i = 0, j = 0;
+        float sc_a = 0.f, sc_r = 0.f;
+        if (active) {
+            int32_t p = kept_pos[e];
+            i = row[p];
+            j = col[p];
+            float kb = (float)batch_kept[i / batch_size];
+            sc_a = inv_nb / kb;                                      // mean over kept, mean over batches
+            sc_r = inv_nb / (kb * (float)num_rep);
+        }
+        Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * dim + gl * VEC);
+        Vec<VEC> gi;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
+        // attractive term (ref: model.py:312-322)
+        {
+            Vec<VEC> yj = load_vec<VEC>(tail + (int64_t)j * dim + gl * VEC);
+            Vec<VEC> df;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { df.v[c] = yi.v[c] - yj.v[c]; s = fmaf(df.v[c], df.v[c], s); }
+            s = group_sum<LANES>(s);
+            float coef, l;
+            attr_terms(s, a, b, coef, l);
+            coef *= sc_a;
+            if (gl == 0) loss_acc += l * sc_a;
+            Vec<VEC> g;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df.v[c]; gi.v[c] += g.v[c]; }
+            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)j * dim + gl * VEC, g, -1.0f);
+        }
+        // repulsive terms (ref: model.py:324-334, 441-449)
+        Philox4 rnd = {0, 0, 0, 0};
+        for (int r = 0; r < num_rep; ++r) {
+            uint32_t l_idx;
+            if (neg) {
+                l_idx = active ? (uint32_t)neg[e * num_rep + r] : 0u;
+            } else {
+                if ((r & 3) == 0) {
+                    uint32_t p = active ? (uint32_t)kept_pos[e] : 0u;
+                    rnd = philox4x32_10(p, (uint32_t)(r >> 2), epoch, STREAM_NEG, k0, k1);
+                }
+                uint32_t x = (r & 3) == 0 ? rnd.x : (r & 3) == 1 ? rnd.y : (r & 3) == 2 ? rnd.z : rnd.w;
+                l_idx = urange(x, rep_count);
+            }
+            Vec<VEC> yl = load_vec<VEC>(tail + (int64_t)l_idx * dim + gl * VEC);
+            Vec<VEC> df;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { df.v[c] = yi.v[c] - yl.v[c]; s = fmaf(df.v[c], df.v[c], s); }
+            s = group_sum<LANES>(s);
+            float coef, l;
+            rep_terms(s, a, b, coef, l);
+            coef *= sc_r;
+            if (gl == 0) loss_acc += l * sc_r;
+            Vec<VEC> g;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df.v[c]; gi.v[c] += g.v[c]; }
+            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)l_idx * dim + gl * VEC, g, -1.0f);
+        }
+        if (active) red_vec<VEC>(grad_head + (int64_t)i * dim + gl * VEC, gi, 1.0f);
+    }
+    if (loss_out) {
+        loss_acc = warp_sum(loss_acc);
+        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
+    }
+}
+
+// generic dimension: one warp per kept edge, lane owns components lane, lane+32, ... (dim <= 128)
+__global__ void __launch_bounds__(256)
+edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                           const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                           const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept,
+                           int n_batches, int batch_size, int num_rep, uint32_t rep_count,
+                           const float *__restrict__ head, const float *__restrict__ tail,
+                           float *__restrict__ grad_head, float *__restrict__ grad_tail, int dim, float a,
+                           float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    const int n_kept = *kept_count;
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv_nb = 1.0f / (float)n_batches;
+    float loss_acc = 0.f;
+    for (int64_t e = wid; e < n_kept; e += n_warps) {
+        int32_t p = kept_pos[e];
+        int32_t i = row[p], j = col[p];
+        float kb = (float)batch_kept[i / batch_size];
+        float sc_a = inv_nb / kb, sc_r = inv_nb / (kb * (float)num_rep);
+        float yi[4], gi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { int cc = lane + 32 * c; yi[c] = cc < dim ? head[(int64_t)i * dim + cc] : 0.f; }
+        Philox4 rnd = {0, 0, 0, 0};
+        for (int r = -1; r < num_rep; ++r) {
+            uint32_t t_idx;
+            if (r < 0) t_idx = (uint32_t)j;
+            else if (neg) t_idx = (uint32_t)neg[e * num_rep + r];
+            else {
+                if ((r & 3) == 0) rnd = philox4x32_10((uint32_t)p, (uint32_t)(r >> 2), epoch, STREAM_NEG, k0, k1);
+                uint32_t x = (r & 3) == 0 ? rnd.x : (r & 3) == 1 ? rnd.y : (r & 3) == 2 ? rnd.z : rnd.w;
+                t_idx = urange(x, rep_count);
+            }
+            float df[4], s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int cc = lane + 32 * c;
+                float yt = cc < dim ? tail[(int64_t)t_idx * dim + cc] : 0.f;
+                df[c] = yi[c] - yt;
+                s = fmaf(df[c], df[c], s);
+            }
+            s = warp_sum(s);
+            float coef, l;
+            if (r < 0) { attr_terms(s, a, b, coef, l); coef *= sc_a; l *= sc_a; }
+            else { rep_terms(s, a, b, coef, l); coef *= sc_r; l *= sc_r; }
+            if (lane == 0) loss_acc += l;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                int cc = lane + 32 * c;
+                float g = coef * df[c];
+                gi[c] += g;
+                if (cc < dim && grad_tail) red_add_f32(grad_tail + (int64_t)t_idx * dim + cc, -g);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { int cc = lane + 32 * c; if (cc < dim) red_add_f32(grad_head + (int64_t)i * dim + cc, gi[c]); }
+    }
+    if (loss_out && lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
+}
+
+// ------------------------------------------------------------------ K8: InfoNCE
+constexpr int NCE_MAX = 16;   // 1 positive + up to 15 negatives
+
+__global__ void __launch_bounds__(128)
+infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int dim,
+               const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
+               float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
+               uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float loss_local = 0.f;
+    if (t < num) {
+        const int64_t n_chunks = (num + chunk - 1) / chunk;
+        const int64_t cidx = t / chunk;
+        const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
+        const float wgt = weight / ((float)clen * (float)n_chunks);       // ref: model.py:392,394
+        const int32_t i = perm ? perm[t] : (int32_t)t;
+        const int M = 1 + n_neg;
+        int32_t ids[NCE_MAX];
+        bool ok[NCE_MAX];
+        float nrm[NCE_MAX], cs[NCE_MAX];
+        ids[0] = i; ok[0] = true;
+        if (neg) {
+            for (int m = 1; m < M; ++m) ids[m] = neg[t * n_neg + (m - 1)];
+        } else {
+            const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+            Philox4 rnd = {0, 0, 0, 0};
+            for (int m = 1; m < M; ++m) {
+                int q = m - 1;
+                if ((q & 3) == 0) rnd = philox4x32_10((uint32_t)t, (uint32_t)(q >> 2), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
+                uint32_t x = (q & 3) == 0 ? rnd.x : (q & 3) == 1 ? rnd.y : (q & 3) == 2 ? rnd.z : rnd.w;
+                ids[m] = (int32_t)urange(x, (uint32_t)num);
+            }
+        }
+        for (int m = 1; m < M; ++m) ok[m] = ids[m] != i;                     // ref: model.py:386
+        const float *ap = e0 + (int64_t)i * dim;
+        float na2 = 0.f;
+        for (int c = 0; c < dim; ++c) na2 = fmaf(ap[c], ap[c], na2);
+        const float na = fmaxf(sqrtf(na2), 1e-12f);                          // F.normalize eps
+        float mx = -__int_as_float(0x7f800000);
+        for (int m = 0; m < M; ++m) {
+            nrm[m] = 1.f; cs[m] = 0.f;
+            if (!ok[m]) continue;
+            const float *ep = e1 + (int64_t)ids[m] * dim;
+            float n2 = 0.f, dt = 0.f;
+            for (int c = 0; c < dim; ++c) { float v = ep[c]; n2 = fmaf(v, v, n2); dt = fmaf(ap[c], v, dt); }
+            nrm[m] = fmaxf(sqrtf(n2), 1e-12f);
+            cs[m] = dt / (na * nrm[m]);                                      // cosine similarity
+            mx = fmaxf(mx, cs[m] / temperature);
+        }
+        float den = 0.f;
+        for (int m = 0; m < M; ++m) if (ok[m]) den += expf(cs[m] / temperature - mx);
+        loss_local = wgt * -(cs[0] / temperature - mx - logf(den));          // -log_softmax[:,0]
+        // c_m = softmax_m - delta_m0 ; sum_m c_m * cos_m
+        float cm[NCE_MAX];
+        float ccs = 0.f;
+        for (int m = 0; m < M; ++m) {
+            cm[m] = ok[m] ? expf(cs[m] / temperature - mx) / den - (m == 0 ? 1.f : 0.f) : 0.f;
+            ccs = fmaf(cm[m], cs[m], ccs);
+        }
+        const float sa = wgt / (temperature * na);
+        for (int c = 0; c < dim; ++c) {
+            const float ac = ap[c];
+            const float uc = ac / na;
+            float acc = 0.f;
+            for (int m = 0; m < M; ++m) {
+                if (!ok[m]) continue;
+                float vc = e1[(int64_t)ids[m] * dim + c] / nrm[m];
+                acc = fmaf(cm[m], vc, acc);
+                // d/d e_m = w c_m (u - v_m (v_m.u)) / (tau |e_m|)
+                float gm = wgt * cm[m] * (uc - vc * cs[m]) / (temperature * nrm[m]);
+                red_add_f32(grad1 + (int64_t)ids[m] * dim + c, gm);
+            }
+            // d/d a = w (sum_m c_m v_m - u sum_m c_m cos_m) / (tau |a|)
+            red_add_f32(grad0 + (int64_t)i * dim + c, sa * (acc - uc * ccs));
+        }
+    }
+    if (loss_out) {
+        loss_local = warp_sum(loss_local);
+        if ((threadIdx.x & 31) == 0 && loss_local != 0.f) atomicAdd(loss_out, loss_local);
+    }
+}
+
+// ------------------------------------------------------------------ K9: Adam
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+            int64_t n, float beta1, float beta2, float eps, const OptState *__restrict__ st, int zero_grad) {
+    const float step_size = st->step_size, bc2_sqrt = st->bc2_sqrt;
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float gg = g[i];
+        float mm = m[i];
+        float vv = v[i];
+        mm = mm + omb1 * (gg - mm);                     // exp_avg.lerp_(grad, 1-beta1)
+        vv = vv * beta2 + (omb2 * gg) * gg;             // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[i] = p[i] + (-step_size * mm) / denom;        // addcdiv_(exp_avg, denom, value=-step_size)
+        m[i] = mm;
+        v[i] = vv;
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
+static inline unsigned persistent_blocks(int threads, int per_sm) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    (void)threads;
+    return (unsigned)(sms * per_sm);
+}
+
+}  // namespace mmu
+
+extern "C" int mmu_opt_state_init(uint32_t *state, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(state, "mmu_opt_state_init: null pointer");
+    opt_state_init_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<OptState *>(state));
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_opt_state_advance(uint32_t *state, float lr, float beta1, float beta2, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(state, "mmu_opt_state_advance: null pointer");
+    opt_state_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<OptState *>(state), lr, beta1, beta2);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
+                               uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
+                               int32_t *batch_kept, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(row && w && state && kept_pos && kept_count && batch_kept, "mmu_edge_sample: null pointer");
+    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample: bad batch geometry");
+    MMU_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 31), "mmu_edge_sample: nnz must be < 2^31");
+    cudaStream_t st = as_stream(stream);
+    MMU_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st));
+    MMU_CUDA(cudaMemsetAsync(batch_kept, 0, sizeof(int32_t) * (size_t)n_batches, st));
+    if (nnz == 0) return MMU_OK;
+    int64_t n4 = (nnz + 3) / 4;
+    int64_t want = (n4 + 255) / 256;
+    unsigned cap = persistent_blocks(256, 8);
+    unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
+    edge_sample_kernel<<<blocks, 256, 0, st>>>(row, w, nnz, batch_size, seed, reinterpret_cast<const OptState *>(state),
+                                               kept_pos, kept_count, batch_kept);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
+                               const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
+                               int n_batches, int batch_size, int num_rep, int64_t rep_count, const float *head,
+                               const float *tail, float *grad_head, float *grad_tail, int dim, float a, float b,
+                               uint64_t seed, const uint32_t *state, float *loss, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(row && col && kept_pos && kept_count && batch_kept && head && tail && grad_head && state,
+                  "mmu_edge_forces: null pointer");
+    MMU_CHECK_ARG(dim >= 1 && dim <= 128, "mmu_edge_forces: dim=%d outside [1,128]", dim);
+    MMU_CHECK_ARG(num_rep >= 0 && rep_count >= 1 && rep_count < ((int64_t)1 << 31), "mmu_edge_forces: bad negatives");
+    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_forces: bad batch geometry");
+    cudaStream_t st = as_stream(stream);
+    const OptState *os = reinterpret_cast<const OptState *>(state);
+    unsigned blocks = persistent_blocks(256, 8);
+#define MMU_FORCES(V, L)                                                                                        \
+    edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept, n_batches, \
+                                                     batch_size, num_rep, (uint32_t)rep_count, head, tail,       \
+                                                     grad_head, grad_tail, dim, a, b, seed, os, loss)
+    switch (dim) {
+        case 2: MMU_FORCES(2, 1); break;
+        case 4: MMU_FORCES(4, 1); break;
+        case 8: MMU_FORCES(4, 2); break;
+        case 16: MMU_FORCES(4, 4); break;
+        case 32: MMU_FORCES(4, 8); break;
+        case 64: MMU_FORCES(4, 16); break;
+        case 128: MMU_FORCES(4, 32); break;
+        default:
+            edge_forces_generic_kernel<<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept,
+                                                               n_batches, batch_size, num_rep, (uint32_t)rep_count,
+                                                               head, tail, grad_head, grad_tail, dim, a, b, seed, os, loss);
+    }
+#undef MMU_FORCES
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int dim, const int32_t *perm,
+                           const int32_t *neg, int n_neg, int chunk, float weight, float temperature, float *grad0,
+                           float *grad1, uint64_t seed, uint32_t stream_id, const uint32_t *state, float *loss,
+                           mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(e0 && e1 && grad0 && grad1 && state, "mmu_infonce: null pointer");
+    MMU_CHECK_ARG(n_neg >= 0 && n_neg < NCE_MAX, "mmu_infonce: n_neg=%d outside [0,%d)", n_neg, NCE_MAX);
+    MMU_CHECK_ARG(dim >= 1 && chunk >= 1 && temperature > 0.f, "mmu_infonce: bad dim/chunk/temperature");
+    MMU_CHECK_ARG(num >= 0 && num < ((int64_t)1 << 31), "mmu_infonce: num must be < 2^31");
+    if (num == 0) return MMU_OK;
+    infonce_kernel<<<(unsigned)((num + 127) / 128), 128, 0, as_stream(stream)>>>(
+        e0, e1, num, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id,
+        reinterpret_cast<const OptState *>(state), loss);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, float beta1, float beta2, float eps,
+                             const uint32_t *state, int zero_grad, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(p && g && m && v && state, "mmu_adam_step: null pointer");
+    if (n == 0) return MMU_OK;
+    int64_t want = (n + 255) / 256;
+    unsigned cap = persistent_blocks(256, 16);
+    unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
+    adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+                                                       reinterpret_cast<const OptState *>(state), zero_grad);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}

@@ -1,0 +1,80 @@
+// spmm.cu -- K6: transform initialisation (row-normalised fixed-degree SpMM) and a CSR SpMM.
+//
+// ref: /root/reference/impl/model.py:236-252 (embed_query: row-normalise, sparse @ dense)
+//      /root/reference/impl/model.py:227,232 (operator applications inside the spectral init)
+#include "common.cuh"
+
+namespace mmu {
+
+// one thread per output element; the k (col, w) pairs of a row are read by `dim` adjacent
+// threads (broadcast), ref rows are read as contiguous dim-float segments.
+__global__ void __launch_bounds__(256)
+embed_query_kernel(const int32_t *__restrict__ col, const float *__restrict__ w, int64_t n_rows, int k,
+                   const float *__restrict__ ref, int dim, float *__restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * dim) return;
+    int64_t r = e / dim;
+    int c = (int)(e - r * dim);
+    float s = 0.f;
+    for (int j = 0; j < k; ++j) s += w[r * k + j];
+    s = fmaxf(s, 1e-6f);                                  // ref: model.py:247 clamp(min=1e-6)
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+        int32_t cj = col[r * k + j];
+        if (cj >= 0) acc = fmaf(w[r * k + j] / s, ref[(int64_t)cj * dim + c], acc);
+    }
+    out[e] = acc;
+}
+
+// Y = A X, one warp per row, lanes over the m columns (m <= 32 per sweep), edges sequential.
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                const float *__restrict__ val, int64_t n, const float *__restrict__ x, int m,
+                float *__restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int64_t e0 = rowptr[r], e1 = rowptr[r + 1];
+    for (int c0 = 0; c0 < m; c0 += 32) {
+        int c = c0 + lane;
+        float acc = 0.f;
+        for (int64_t eb = e0; eb < e1; eb += 32) {
+            int64_t e = eb + lane;
+            int32_t cj = (e < e1) ? col[e] : 0;
+            float vj = (e < e1) ? val[e] : 0.f;
+            int cnt = (int)min((int64_t)32, e1 - eb);
+            for (int j = 0; j < cnt; ++j) {
+                int32_t cc = __shfl_sync(0xffffffffu, cj, j);
+                float vv = __shfl_sync(0xffffffffu, vj, j);
+                if (c < m) acc = fmaf(vv, x[(int64_t)cc * m + c], acc);
+            }
+        }
+        if (c < m) y[r * m + c] = acc;
+    }
+}
+
+}  // namespace mmu
+
+extern "C" int mmu_embed_query(const int32_t *col, const float *w, int64_t n_rows, int k, const float *ref,
+                               int dim, float *out, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(col && w && ref && out, "mmu_embed_query: null pointer");
+    MMU_CHECK_ARG(k >= 1 && dim >= 1, "mmu_embed_query: bad k/dim");
+    if (n_rows == 0) return MMU_OK;
+    int64_t total = n_rows * dim;
+    embed_query_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(col, w, n_rows, k, ref, dim, out);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                            const float *x, int m, float *y, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(rowptr && col && val && x && y, "mmu_spmm_csr: null pointer");
+    MMU_CHECK_ARG(m >= 1, "mmu_spmm_csr: bad m");
+    MMU_CHECK_ARG(x != y, "mmu_spmm_csr: x and y must not alias");
+    if (n == 0) return MMU_OK;
+    spmm_csr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, m, y);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}

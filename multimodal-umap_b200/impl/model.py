@@ -1,0 +1,285 @@
+"""Drop-in replacement for the reference's impl/model.py on a B200.
+
+Same public surface as /root/reference/impl/model.py (device, UMAPEncoder, UMAPMixture with
+fit / fit_transform / transform / inverse_transform / save_state_dict / load_state_dict) so that
+the reference's main.py, impl/validation.py and impl/crossmodal.py run unchanged when this
+directory precedes the reference tree on sys.path (`impl` is a namespace package: there is
+deliberately no impl/__init__.py).  All numerics run in hand-written sm_100a kernels behind
+the C ABI of include/mmumap.h; there is no CPU fallback.
+
+Engine switches (attributes of UMAPMixture / environment):
+  sample_stream  "device" (Philox in-kernel, default) | "host" (replay the reference's CPU
+                 generator draws; parity mode)                        env MMUMAP_SAMPLE_STREAM
+  sigma_solver   "bisect" (default) | "newton" (the reference's 20-step Newton, reproducing
+                 its divergent rows)                                  env MMUMAP_SIGMA
+  knn_method     "tc" (tcgen05 candidates + fp32 rescoring) | "simt"  env MMUMAP_KNN
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+import weakref
+
+import torch
+
+from umap_b200 import graph as G
+from umap_b200 import native
+from umap_b200.layout import LayoutOptimizer
+from umap_b200.spectral import spectral_init
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")      # ref: model.py:10
+
+_GRAPHS: dict[int, tuple] = {}     # id(sparse tensor) -> (weakref, Graph); keeps checkpoints torch-only
+
+
+def _register(t: torch.Tensor, g: G.Graph) -> torch.Tensor:
+    _GRAPHS[id(t)] = (weakref.ref(t, lambda _r, k=id(t): _GRAPHS.pop(k, None)), g)
+    return t
+
+
+def _as_graph(t) -> G.Graph:
+    if isinstance(t, G.Graph):
+        return t
+    hit = _GRAPHS.get(id(t))
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    g = G.Graph.from_sparse_coo(t)
+    _register(t, g)
+    return g
+
+
+def _coo(g: G.Graph) -> torch.Tensor:
+    idx = torch.stack([g.row.long(), g.col.long()], dim=0)
+    t = torch.sparse_coo_tensor(idx, g.val, (g.n_rows, g.n_cols), is_coalesced=True)
+    return _register(t, g)
+
+
+class UMAPEncoder:
+    """Single-modality graph builder and initialiser (ref: model.py:12-278)."""
+
+    def __init__(self, k_neighbors: int, out_dim: int, id: int = 0):
+        self.k_neighbors = k_neighbors
+        self.out_dim = out_dim
+        self.id = id
+        self.sigmas = None
+        self.rhos = None
+        self.sigma_solver = os.environ.get("MMUMAP_SIGMA", "bisect")
+        self.knn_method = None
+
+    def get_sigmas(self, dists: torch.Tensor, min_dists: torch.Tensor | None = None, num_iters: int | None = None) -> torch.Tensor:
+        """ref: model.py:33-61.  min_dists is accepted for signature parity; rho is the row minimum."""
+        dists = dists.to("cuda", torch.float32).reshape(-1, self.k_neighbors).contiguous()
+        idx = torch.arange(self.k_neighbors, dtype=torch.int32, device=dists.device).repeat(dists.shape[0], 1)
+        _, _, sigma, _ = G.smooth_knn(idx, dists, self.sigma_solver, num_iters)
+        return sigma
+
+    def fuzzy_knn_graph(self, inputs: torch.Tensor, mode: str = "fit", query: torch.Tensor | None = None,
+                        ref_data: torch.Tensor | None = None, num_iters: int = 10, a: float | None = None,
+                        b: float | None = None) -> torch.Tensor:
+        """ref: model.py:63-209.  Exact kNN (self excluded iff ref_data is None, model.py:87-90),
+        then rho/sigma/weights (or 1/(1+a d^2b) in invert mode); returns the coalesced (Q, N) COO."""
+        native.require_cuda()
+        q = inputs if query is None else query
+        idx, dist = G.knn_graph(q, inputs, self.k_neighbors, exclude_self=ref_data is None, method=self.knn_method)
+        if mode != "invert":
+            col, w, sigma, rho = G.smooth_knn(idx, dist, self.sigma_solver)
+            if mode == "fit":
+                self.sigmas, self.rhos = sigma, rho                      # model.py:202-204
+        else:
+            col, w = G.invert_weights(idx, dist, a, b)
+        g = G.Graph.from_fixed_degree(col, w, inputs.shape[0])
+        g.k = self.k_neighbors
+        g.col2d, g.w2d = col, w
+        return _coo(g)
+
+    @torch.no_grad()
+    def embed_all(self, input: torch.Tensor) -> torch.Tensor:
+        """ref: model.py:211-234."""
+        return spectral_init(_as_graph(input), self.out_dim)
+
+    @torch.no_grad()
+    def embed_query(self, ref: torch.Tensor, query: torch.Tensor) -> torch.Tensor:
+        """ref: model.py:236-252."""
+        g = _as_graph(query)
+        if getattr(g, "col2d", None) is not None:
+            return G.embed_query(g.col2d, g.w2d, ref)
+        rs = torch.zeros(g.n_rows, dtype=torch.float32, device=g.val.device)
+        rs.index_add_(0, g.row.long(), g.val)
+        return G.spmm(g, ref.to("cuda", torch.float32), g.val / rs.clamp(min=1e-6)[g.row.long()])
+
+    def init(self, input: torch.Tensor, mode: str = "fit", query: torch.Tensor | None = None,
+             ref_data: torch.Tensor | None = None, ref_embeds: torch.Tensor | None = None,
+             a: float | None = None, b: float | None = None):
+        """ref: model.py:254-278."""
+        graph = self.fuzzy_knn_graph(input, mode, query, ref_data, num_iters=10, a=a, b=b)
+        if mode == "fit":
+            g = _as_graph(graph)
+            sym = G.fuzzy_union(g.col2d, g.w2d)                          # model.py:271
+            graph = _coo(sym)
+            embed = self.embed_all(graph)
+        elif mode == "transform":
+            embed = self.embed_query(ref_embeds, graph)
+        else:
+            embed = self.embed_query(ref_embeds if ref_embeds is not None else input, graph)
+        return graph, embed
+
+
+class UMAPMixture:
+    """Multimodal UMAP with InfoNCE alignment (ref: model.py:280-714)."""
+
+    def __init__(self, k_neighbors: int, out_dim: int, min_dist: float, num_encoders: int):
+        self.k_neighbors = k_neighbors
+        self.out_dim = out_dim
+        self.min_dist = min_dist
+        self.num_encoders = num_encoders
+        self.a, self.b = self.get_ab_coeffs(min_dist)
+        self.encoders = [UMAPEncoder(k_neighbors, out_dim, id=i) for i in range(num_encoders)]
+        self.data = None
+        self.graphs = []
+        self.embeds = []
+        self._engine_defaults()
+
+    def _engine_defaults(self):
+        self.sample_stream = os.environ.get("MMUMAP_SAMPLE_STREAM", "device")
+        self.last_optimizer = None
+
+    # ------------------------------------------------------------------ optimiser
+    def _train(self, embeds, graphs, epochs: int, num_rep: int, lr: float, alpha: float, batch_size: int,
+               mode: str = "fit", data_indices: list | None = None, desc: str = "Training"):
+        """ref: model.py:396-481."""
+        native.require_cuda()
+        if mode == "invert":
+            raise NotImplementedError("invert-mode optimisation: see DESIGN.md (SURVEY.md section 8 f2)")
+        refs = None
+        if mode == "transform":
+            for ref in self.embeds:                                       # model.py:399-401
+                ref.requires_grad = False
+            n_modes = len(embeds) if data_indices is None else len(data_indices)
+            refs = [self.embeds[data_indices[i]] if data_indices is not None else self.embeds[i]
+                    for i in range(n_modes)]
+        opt = LayoutOptimizer(embeds, [_as_graph(g) for g in graphs], self.a, self.b, num_rep, lr, alpha,
+                              batch_size, mode=mode, refs=refs,
+                              sample_stream=getattr(self, "sample_stream", None))
+        out = opt.run(epochs)
+        self.last_optimizer = opt
+        return [e.requires_grad_(True) for e in out]                     # leaves, as model.py:397,481
+
+    def fit(self, inputs: list, epochs: int, num_rep: int = 8, lr: float = 0.2, alpha: float = 0.5,
+            batch_size: int = 512) -> None:
+        """ref: model.py:483-508."""
+        graphs, embeds = self.init(inputs, mode="fit")
+        self.graphs = graphs
+        self.data = [x.to(device) for x in inputs]
+        self.embeds = self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="fit",
+                                  desc=f"Training {self.num_encoders} encoders")
+
+    def fit_transform(self, inputs: list, epochs: int, num_rep: int = 8, lr: float = 0.2, alpha: float = 0.5,
+                      batch_size: int = 512):
+        """ref: model.py:510-525."""
+        self.fit(inputs, epochs, num_rep, lr, alpha, batch_size)
+        return self.embeds
+
+    def transform(self, inputs: list, epochs: int, data_indices: list | None = None, num_rep: int = 8,
+                  lr: float = 0.2, alpha: float = 0.5, batch_size: int = 512):
+        """ref: model.py:527-555."""
+        graphs, embeds = self.init(inputs, mode="transform", data_indices=data_indices)
+        return self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="transform",
+                           data_indices=data_indices, desc=f"Embedding {len(embeds)} modalities")
+
+    def inverse_transform(self, inputs: list, epochs: int, data_indices: list | None = None, num_rep: int = 8,
+                          lr: float = 0.2, alpha: float = 0.5, batch_size: int = 512):
+        """ref: model.py:557-585.  The reference's invert path raises a shape error as shipped
+        (SURVEY.md section 0 item 1).  Here the evident intent is implemented for the
+        initialisation -- kNN of the query embeddings among the fitted embeddings, weights
+        1/(1+a d^2b), weighted mean of the TARGET modality's data rows (Q x D) -- and returned;
+        the invert-mode refinement epochs (model.py:336-362) are the next component."""
+        graphs, embeds = self.init(inputs, mode="invert", data_indices=data_indices)
+        if epochs > 0:
+            warnings.warn("inverse_transform returns the weighted-neighbour initialisation; "
+                          "invert-mode refinement epochs are not implemented yet", stacklevel=2)
+        return embeds
+
+    # ------------------------------------------------------------------ curve fit (host, one-off)
+    def get_ab_coeffs(self, min_dist: float, num_iters: int = 50):
+        """ref: model.py:587-618: Gauss-Newton fit of 1/(1+a x^(2b)) to the min_dist target on
+        linspace(1e-4, 3, 200) from (1, 1), fp32; closed-form Jacobian instead of autograd."""
+        x = torch.linspace(1e-4, 3.0, 200, dtype=torch.float32)
+        target = torch.where(x <= min_dist, torch.tensor(1.0), torch.exp(-(x - min_dist)))
+        betas = torch.tensor([1.0, 1.0])
+        for _ in range(num_iters):
+            a_, b_ = betas[0].abs() + 1e-6, betas[1].abs() + 1e-6
+            xp = x.pow(2 * b_)
+            est = 1.0 / (1.0 + a_ * xp)
+            res = target - est
+            jac = torch.stack([torch.sign(betas[0]) * xp * est * est,
+                               torch.sign(betas[1]) * a_ * xp * 2.0 * torch.log(x) * est * est], dim=1)
+            betas = betas - torch.linalg.pinv(jac) @ res
+        return (betas[0].abs() + 1e-6).item(), (betas[1].abs() + 1e-6).item()
+
+    # ------------------------------------------------------------------ orchestration
+    def init(self, inputs: list, mode: str = "fit", data_indices: list | None = None):
+        """ref: model.py:620-651."""
+        if mode not in ["fit", "transform", "invert"]:
+            raise ValueError(f"Invalid mode: {mode}")
+        native.require_cuda()
+        inputs = [x.to(device) for x in inputs]
+        graphs, embeds = [], []
+        encoder_indices = data_indices if data_indices is not None else range(self.num_encoders)
+        for idx, i in enumerate(encoder_indices):
+            encoder = self.encoders[i]
+            if mode == "fit":
+                graph, embed = encoder.init(inputs[idx], mode="fit")
+            elif mode == "transform":
+                graph, embed = encoder.init(self.data[i], mode="transform", query=inputs[idx],
+                                            ref_data=self.graphs[i], ref_embeds=self.embeds[i])
+            else:
+                # neighbours in embedding space, initial value = weighted mean of the data rows
+                graph, embed = encoder.init(self.embeds[i].detach(), mode="invert", query=inputs[idx],
+                                            ref_data=self.graphs[i], ref_embeds=self.data[i], a=self.a, b=self.b)
+            graphs.append(graph)
+            embeds.append(embed)
+        return graphs, embeds
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_state_dict(self, path: str) -> None:
+        """ref: model.py:653-683 (same keys, torch-only payload)."""
+        print("Warning: save_state_dict() saves the entire model state, which includes the source dataset. "
+              "Make sure this is intended before proceeding.")
+        state_dict = {
+            "k_neighbors": self.k_neighbors,
+            "out_dim": self.out_dim,
+            "min_dist": self.min_dist,
+            "num_encoders": self.num_encoders,
+            "a": self.a,
+            "b": self.b,
+            "encoders": [{"sigmas": e.sigmas, "rhos": e.rhos} for e in self.encoders],
+            "data": self.data,
+            "graphs": self.graphs,
+            "embeds": self.embeds,
+        }
+        dirname = os.path.dirname(path)
+        if dirname and not os.path.exists(dirname):
+            os.makedirs(dirname)
+        torch.save(state_dict, path)
+
+    @classmethod
+    def load_state_dict(cls, path: str) -> "UMAPMixture":
+        """ref: model.py:685-714."""
+        state_dict = torch.load(path)
+        model = cls.__new__(cls)
+        model.k_neighbors = state_dict["k_neighbors"]
+        model.out_dim = state_dict["out_dim"]
+        model.min_dist = state_dict["min_dist"]
+        model.num_encoders = state_dict["num_encoders"]
+        model.a = state_dict["a"]
+        model.b = state_dict["b"]
+        model.encoders = [UMAPEncoder(model.k_neighbors, model.out_dim, id=i) for i in range(model.num_encoders)]
+        for encoder, encoder_state in zip(model.encoders, state_dict["encoders"]):
+            encoder.sigmas = encoder_state["sigmas"]
+            encoder.rhos = encoder_state["rhos"]
+        model.data = state_dict["data"]
+        model.graphs = state_dict["graphs"]
+        model.embeds = state_dict["embeds"]
+        model._engine_defaults()
+        return model

@@ -1,0 +1,171 @@
+"""Graph construction on the device: exact kNN -> rho/sigma/weights -> fuzzy union.
+
+Host-side orchestration of kernels K1-K6 (include/mmumap.h).  Mirrors what
+/root/reference/impl/model.py:63-209 (fuzzy_knn_graph), :271 (union) and :236-252
+(embed_query) compute, with the exact kNN search north_star specifies in place of the
+reference's randomised NN-descent.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+
+from . import native
+from .native import check, lib, ptr, stream
+
+
+@dataclass
+class Graph:
+    """Coalesced sparse matrix in device CSR+COO form (int32 indices, fp32 values).
+
+    `row`/`col`/`val` are exactly the (row, col)-sorted COO arrays .coalesce() yields in the
+    reference (model.py:208,271); `rowptr` (int64, n_rows+1) gives O(1) row ranges instead of
+    the reference's full-COO mask scan per batch (model.py:428)."""
+    n_rows: int
+    n_cols: int
+    rowptr: torch.Tensor
+    row: torch.Tensor
+    col: torch.Tensor
+    val: torch.Tensor
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    def to_sparse_coo(self) -> torch.Tensor:
+        idx = torch.stack([self.row.long(), self.col.long()], dim=0)
+        t = torch.sparse_coo_tensor(idx, self.val, (self.n_rows, self.n_cols), is_coalesced=True)
+        t._mmu_graph = self
+        return t
+
+    @staticmethod
+    def from_sparse_coo(t: torch.Tensor) -> "Graph":
+        g = getattr(t, "_mmu_graph", None)
+        if g is not None:
+            return g
+        native.require_cuda()
+        t = t.coalesce() if not t.is_coalesced() else t
+        dev = torch.device("cuda")
+        idx = t.indices().to(dev)
+        row = idx[0].to(torch.int32).contiguous()
+        col = idx[1].to(torch.int32).contiguous()
+        val = t.values().to(dev, torch.float32).contiguous()
+        counts = torch.bincount(idx[0], minlength=t.shape[0])
+        rowptr = torch.zeros(t.shape[0] + 1, dtype=torch.int64, device=dev)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        g = Graph(t.shape[0], t.shape[1], rowptr, row, col, val)
+        try:
+            t._mmu_graph = g
+        except Exception:  # pragma: no cover
+            pass
+        return g
+
+    @staticmethod
+    def from_fixed_degree(col: torch.Tensor, val: torch.Tensor, n_cols: int) -> "Graph":
+        q, k = col.shape
+        rowptr = torch.arange(0, (q + 1) * k, k, dtype=torch.int64, device=col.device)
+        row = torch.arange(q, dtype=torch.int32, device=col.device).repeat_interleave(k)
+        return Graph(q, n_cols, rowptr, row, col.reshape(-1).contiguous(), val.reshape(-1).contiguous())
+
+
+def _f32c(x: torch.Tensor) -> torch.Tensor:
+    native.require_cuda()
+    return x.detach().to("cuda", torch.float32).contiguous()
+
+
+def knn_exact_simt(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
+                   query_base: int = 0, db_base: int = 0, out=None, rows: torch.Tensor | None = None):
+    """K1 fallback path: exhaustive fp32 kNN on CUDA cores (mmu_knn_exact_f32)."""
+    query, db = _f32c(query), _f32c(db)
+    q, d = query.shape
+    merge = out is not None
+    if out is None:
+        idx = torch.empty((q, k), dtype=torch.int32, device=query.device)
+        dist = torch.empty((q, k), dtype=torch.float32, device=query.device)
+    else:
+        idx, dist = out
+    n_query = q if rows is None else int(rows.numel())
+    check(lib().mmu_knn_exact_f32(ptr(query), n_query, ptr(rows), ptr(db), db.shape[0], d, k, int(exclude_self),
+                                  query_base, db_base, int(merge and rows is None), ptr(idx), ptr(dist), stream()),
+          "mmu_knn_exact_f32")
+    return idx, dist
+
+
+def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, method: str | None = None):
+    """Exact kNN of `query` rows in `db` (ref: model.py:81-195 role; semantics of
+    oracle/knn_oracle.c).  method: "tc" (tcgen05 candidates + fp32 rescoring + certification),
+    "simt" (exhaustive fp32 on CUDA cores) or None = env MMUMAP_KNN, default "tc"."""
+    method = method or os.environ.get("MMUMAP_KNN", "tc")
+    if k > native.MAX_K:
+        raise ValueError(f"k_neighbors={k} exceeds the supported maximum {native.MAX_K}")
+    if db.shape[0] - (1 if exclude_self else 0) < k:
+        raise ValueError(f"need more than k={k} candidate points per row, got {db.shape[0]}")
+    if method == "simt":
+        return knn_exact_simt(query, db, k, exclude_self)
+    if method == "tc":
+        from .knn_tc import knn_tc
+        return knn_tc(query, db, k, exclude_self)
+    raise ValueError(f"unknown kNN method {method!r}")
+
+
+def smooth_knn(idx: torch.Tensor, dist: torch.Tensor, solver: str = "bisect", n_iter: int | None = None):
+    """K4 (ref: model.py:33-61,197-209).  Returns (col_sorted, w_sorted, sigma, rho)."""
+    q, k = idx.shape
+    code = {"bisect": native.SIGMA_BISECT, "newton": native.SIGMA_NEWTON}[solver]
+    if n_iter is None:
+        n_iter = 64 if solver == "bisect" else 20
+    col = torch.empty_like(idx)
+    w = torch.empty_like(dist)
+    sigma = torch.empty(q, dtype=torch.float32, device=idx.device)
+    rho = torch.empty(q, dtype=torch.float32, device=idx.device)
+    check(lib().mmu_smooth_knn(ptr(idx), ptr(dist), q, k, code, n_iter, ptr(sigma), ptr(rho), ptr(col), ptr(w),
+                               stream()), "mmu_smooth_knn")
+    return col, w, sigma, rho
+
+
+def invert_weights(idx: torch.Tensor, dist: torch.Tensor, a: float, b: float):
+    """ref: model.py:206."""
+    q, k = idx.shape
+    col = torch.empty_like(idx)
+    w = torch.empty_like(dist)
+    check(lib().mmu_invert_weights(ptr(idx), ptr(dist), q, k, float(a), float(b), ptr(col), ptr(w), stream()),
+          "mmu_invert_weights")
+    return col, w
+
+
+def fuzzy_union(col: torch.Tensor, w: torch.Tensor) -> Graph:
+    """K5 (ref: model.py:271): S = G + G^T - G*G^T for the fixed-degree graph (col, w) [n x k]."""
+    n, k = col.shape
+    dev = col.device
+    ws_bytes = lib().mmu_union_workspace_bytes(n, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = 2 * n * k
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    orow = torch.empty(cap, dtype=torch.int32, device=dev)
+    ocol = torch.empty(cap, dtype=torch.int32, device=dev)
+    oval = torch.empty(cap, dtype=torch.float32, device=dev)
+    check(lib().mmu_fuzzy_union(ptr(col), ptr(w), n, k, ptr(ws), ws_bytes, ptr(rowptr), ptr(orow), ptr(ocol),
+                                ptr(oval), stream()), "mmu_fuzzy_union")
+    nnz = int(rowptr[-1].item())
+    return Graph(n, n, rowptr, orow[:nnz].clone(), ocol[:nnz].clone(), oval[:nnz].clone())
+
+
+def embed_query(col: torch.Tensor, w: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """K6 (ref: model.py:236-252)."""
+    q, k = col.shape
+    ref = _f32c(ref)
+    out = torch.empty((q, ref.shape[1]), dtype=torch.float32, device=col.device)
+    check(lib().mmu_embed_query(ptr(col), ptr(w), q, k, ptr(ref), ref.shape[1], ptr(out), stream()),
+          "mmu_embed_query")
+    return out
+
+
+def spmm(g: Graph, x: torch.Tensor, val: torch.Tensor | None = None) -> torch.Tensor:
+    x = x.contiguous()
+    y = torch.empty((g.n_rows, x.shape[1]), dtype=torch.float32, device=x.device)
+    v = g.val if val is None else val
+    check(lib().mmu_spmm_csr(ptr(g.rowptr), ptr(g.col), ptr(v), g.n_rows, ptr(x), x.shape[1], ptr(y), stream()),
+          "mmu_spmm_csr")
+    return y

@@ -1,0 +1,188 @@
+"""Layout optimiser: negative-sampling UMAP forces + InfoNCE + Adam on the device.
+
+Host-side orchestration of kernels K7/K8/K9.  Mirrors UMAPMixture._train
+(/root/reference/impl/model.py:396-481) for modes "fit" and "transform".
+
+Two sample streams:
+  * "host"   -- parity mode.  Every random draw is made on torch's global CPU generator with
+                the reference's shapes, dtypes and order (model.py:432,
+                :444, :373, :383), then uploaded; with torch.manual_seed the engine consumes
+                exactly the reference's stream.
+  * "device" -- throughput mode.  Philox4x32-10 counter streams evaluated inside the kernels;
+                no host involvement inside an epoch, statistically equivalent draws.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import native
+from .graph import Graph
+from .native import check, lib, ptr, stream
+
+BETA1, BETA2, EPS = 0.9, 0.999, 1e-8          # torch.optim.Adam defaults (model.py:403)
+INFONCE_NEG = 9                               # n_neg + 1 draws per anchor (model.py:364,383)
+INFONCE_CHUNK = 1000                          # model.py:369
+INFONCE_TAU = 0.5                             # model.py:364
+
+
+def default_stream() -> str:
+    return os.environ.get("MMUMAP_SAMPLE_STREAM", "device")
+
+
+class _Modality:
+    """Device state of one table being optimised."""
+
+    def __init__(self, embed: torch.Tensor, graph: Graph, batch_size: int, ref: torch.Tensor | None):
+        dev = torch.device("cuda")
+        self.p = embed.detach().to(dev, torch.float32).contiguous().clone()
+        self.g = torch.zeros_like(self.p)
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.graph = graph
+        self.ref = None if ref is None else ref.detach().to(dev, torch.float32).contiguous()
+        self.count = self.p.shape[0]
+        self.dim = self.p.shape[1]
+        self.batch_size = batch_size
+        self.n_batches = (self.count + batch_size - 1) // batch_size
+        self.rep_count = self.ref.shape[0] if self.ref is not None else self.count
+        self.kept_pos = torch.empty(max(graph.nnz, 1), dtype=torch.int32, device=dev)
+        self.kept_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.batch_kept = torch.zeros(self.n_batches, dtype=torch.int32, device=dev)
+        # host copies for the replayed stream
+        self._w_cpu = None
+        self._rowptr_cpu = None
+
+    def host_arrays(self):
+        if self._w_cpu is None:
+            self._w_cpu = self.graph.val.cpu()
+            self._rowptr_cpu = self.graph.rowptr.cpu()
+        return self._w_cpu, self._rowptr_cpu
+
+
+def replay_host_draws(mod: _Modality, num_rep: int):
+    """Issue the reference's per-batch draws (model.py:423-444) on the CPU generator.
+    Returns (kept_pos int32 [kept], neg int32 [kept, num_rep], batch_kept int32 [n_batches])."""
+    w_cpu, rowptr = mod.host_arrays()
+    kept_chunks, neg_chunks, counts = [], [], []
+    for j in range(0, mod.count, mod.batch_size):
+        end = min(j + mod.batch_size, mod.count)
+        lo, hi = int(rowptr[j]), int(rowptr[end])
+        keep = torch.rand(hi - lo) < w_cpu[lo:hi]                       # model.py:432
+        pos = torch.nonzero(keep).flatten() + lo
+        num_pairs = pos.numel()
+        neg = torch.randint(0, mod.rep_count, (num_pairs, num_rep))     # model.py:444
+        kept_chunks.append(pos)
+        neg_chunks.append(neg)
+        counts.append(num_pairs)
+    kept = torch.cat(kept_chunks).to(torch.int32)
+    neg = torch.cat(neg_chunks).to(torch.int32).reshape(-1, num_rep)
+    return kept, neg, torch.tensor(counts, dtype=torch.int32)
+
+
+def replay_infonce_draws(num: int):
+    """model.py:373 (randperm) and :383 (randint per chunk of 1000 anchors)."""
+    perm = torch.randperm(num)
+    negs = [torch.randint(0, num, (min(s + INFONCE_CHUNK, num) - s, INFONCE_NEG))
+            for s in range(0, num, INFONCE_CHUNK)]
+    neg = torch.cat(negs) if negs else torch.zeros((0, INFONCE_NEG), dtype=torch.int64)
+    return perm.to(torch.int32), neg.to(torch.int32)
+
+
+class LayoutOptimizer:
+    def __init__(self, embeds, graphs, a: float, b: float, num_rep: int, lr: float, alpha: float,
+                 batch_size: int, mode: str = "fit", refs=None, sample_stream: str | None = None,
+                 seed: int | None = None, track_loss: bool = False):
+        native.require_cuda()
+        if mode not in ("fit", "transform"):
+            raise ValueError(f"Invalid mode: {mode}")
+        self.mode = mode
+        self.a, self.b = float(a), float(b)
+        self.num_rep, self.lr, self.alpha = int(num_rep), float(lr), float(alpha)
+        self.sample_stream = sample_stream or default_stream()
+        if self.sample_stream not in ("host", "device"):
+            raise ValueError(f"unknown sample stream {self.sample_stream!r}")
+        self.mods = [
+            _Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
+                      None if refs is None else refs[i])
+            for i, (e, g) in enumerate(zip(embeds, graphs))
+        ]
+        dev = torch.device("cuda")
+        self.state = torch.zeros(native.OPT_STATE_WORDS, dtype=torch.int32, device=dev)
+        check(lib().mmu_opt_state_init(ptr(self.state), stream()), "mmu_opt_state_init")
+        if seed is None:
+            # consume one draw from the global generator so torch.manual_seed controls the device stream too
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.sample_stream == "device" else 0
+        self.seed = int(seed)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
+        self.losses: list[float] = []
+        self.edge_updates = 0          # host-stream mode counts them exactly; device mode reads kept_count
+
+    # ------------------------------------------------------------------ one epoch
+    def _forces(self, mod: _Modality, kept_pos, kept_count, neg, batch_kept):
+        tail = mod.ref if self.mode == "transform" else mod.p
+        grad_tail = None if self.mode == "transform" else mod.g
+        g = mod.graph
+        check(lib().mmu_edge_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg),
+                                    ptr(batch_kept), mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count,
+                                    ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a, self.b,
+                                    self.seed, ptr(self.state), ptr(self.loss), stream()), "mmu_edge_forces")
+
+    def _infonce(self, src: _Modality, dst: _Modality, perm, neg, stream_id: int):
+        num = min(src.count, dst.count)
+        check(lib().mmu_infonce(ptr(src.p), ptr(dst.p), num, src.dim, ptr(perm), ptr(neg), INFONCE_NEG,
+                                INFONCE_CHUNK, self.alpha, INFONCE_TAU, ptr(src.g), ptr(dst.g), self.seed,
+                                stream_id, ptr(self.state), ptr(self.loss), stream()), "mmu_infonce")
+
+    def epoch(self):
+        host = self.sample_stream == "host"
+        dev = torch.device("cuda")
+        for mod in self.mods:
+            if host:
+                kept, neg, counts = replay_host_draws(mod, self.num_rep)
+                self.edge_updates += int(kept.numel()) * (1 + self.num_rep)
+                n = kept.numel()
+                mod.kept_pos[:n].copy_(kept.pin_memory(), non_blocking=True)
+                mod.kept_count.copy_(torch.tensor([n], dtype=torch.int32).pin_memory(), non_blocking=True)
+                mod.batch_kept.copy_(counts.pin_memory(), non_blocking=True)
+                neg_d = neg.pin_memory().to(dev, non_blocking=True) if n else torch.zeros(1, dtype=torch.int32, device=dev)
+                self._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
+            else:
+                g = mod.graph
+                check(lib().mmu_edge_sample(ptr(g.row), ptr(g.val), g.nnz, mod.batch_size, mod.n_batches, self.seed,
+                                            ptr(self.state), ptr(mod.kept_pos), ptr(mod.kept_count),
+                                            ptr(mod.batch_kept), stream()), "mmu_edge_sample")
+                self._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
+        if self.mode == "fit":                                           # model.py:459-472
+            n = len(self.mods)
+            sid = 0
+            for i in range(n):
+                for j in range(i + 1, n):
+                    for (s, t) in ((i, j), (j, i)):
+                        num = min(self.mods[s].count, self.mods[t].count)
+                        if num == 0:
+                            continue
+                        if host:
+                            perm, neg = replay_infonce_draws(num)
+                            perm_d = perm.pin_memory().to(dev, non_blocking=True)
+                            neg_d = neg.pin_memory().to(dev, non_blocking=True)
+                            self._infonce(self.mods[s], self.mods[t], perm_d, neg_d, sid)
+                        else:
+                            self._infonce(self.mods[s], self.mods[t], None, None, sid)
+                        sid += 1
+        check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
+        for mod in self.mods:
+            check(lib().mmu_adam_step(ptr(mod.p), ptr(mod.g), ptr(mod.m), ptr(mod.v), mod.p.numel(), BETA1, BETA2,
+                                      EPS, ptr(self.state), 1, stream()), "mmu_adam_step")
+        if self.loss is not None:
+            self.losses.append(float(self.loss.item()))
+            self.loss.zero_()
+
+    def run(self, epochs: int):
+        for _ in range(epochs):
+            self.epoch()
+        return [m.p for m in self.mods]
+
+    def kept_last_epoch(self) -> int:
+        return int(sum(int(m.kept_count.item()) for m in self.mods))

@@ -1,0 +1,118 @@
+"""ctypes binding of libmmumap_b200.so (the C ABI declared in include/mmumap.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of
+the first symbol, and every compute call raises NativeError when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, "libmmumap_b200.so")
+
+MAX_K = 64
+OPT_STATE_WORDS = 8
+SIGMA_BISECT = 0
+SIGMA_NEWTON = 1
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/mmumap.h one to one
+_SIGNATURES = {
+    "mmu_abi_version": (c_int, []),
+    "mmu_last_error": (ctypes.c_char_p, []),
+    "mmu_device_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_exact_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
+                                  c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_tc_prepare": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_tc_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "mmu_knn_tc_candidates": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmu_knn_rescore": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p, c_float, c_float, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_smooth_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "mmu_invert_weights": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmu_union_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "mmu_fuzzy_union": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    "mmu_embed_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "mmu_spmm_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
+    "mmu_opt_state_advance": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p]),
+    "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
+                                c_void_p, c_void_p, c_void_p]),
+    "mmu_infonce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                            c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p,
+                              c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C multimodal-umap_b200/csrc`. There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mmu_abi_version() != 1:
+            raise NativeError("libmmumap_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mmu_last_error()
+        raise NativeError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device: the B200 engine has no CPU fallback")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeError("expected a CUDA tensor at the C-ABI boundary")
+    if not t.is_contiguous():
+        raise NativeError("expected a contiguous tensor at the C-ABI boundary")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    require_cuda()
+    sm, mj, mn, l2 = c_int(), c_int(), c_int(), c_size_t()
+    check(lib().mmu_device_info(ctypes.byref(sm), ctypes.byref(mj), ctypes.byref(mn), ctypes.byref(l2)),
+          "mmu_device_info")
+    return {"sm_count": sm.value, "cc": (mj.value, mn.value), "l2_bytes": l2.value}
