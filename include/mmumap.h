@@ -72,44 +72,6 @@ int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_
                   const float *dist_b, int64_t n_rows, int k, int32_t *out_idx, float *out_dist,
                   mmu_stream_t stream);
 
-/* K1 tensor-core candidate generation (tcgen05 / TMEM / TMA), see mmu_knn_tc_* below. */
-
-/* Prepare operands for the tensor-core path: split fp32 rows into bf16 hi/lo parts laid
- * out [rows_padded x dim_padded] (dim_padded multiple of 64, zero filled) and fp32 squared
- * norms.  lo may be NULL (single-pass bf16). */
-int mmu_knn_tc_prepare(const float *x, int64_t n_rows, int dim, int64_t rows_padded, int dim_padded,
-                       void *hi_bf16, void *lo_bf16, float *sqnorm, mmu_stream_t stream);
-
-/* Bytes of scratch mmu_knn_tc_candidates needs. */
-size_t mmu_knn_tc_workspace_bytes(int64_t n_query_padded, int n_cand);
-
-/* K1: for every query row produce n_cand (<= 64) candidate db indices with the smallest
- * approximate squared distance  |q|^2 + |y|^2 - 2 q.y  (q.y from bf16 tensor-core MMAs with
- * fp32 accumulation in TMEM; passes = 1: hi.hi, passes = 3: hi.hi + hi.lo + lo.hi), and the
- * n_cand-th smallest approximate value as `cand_bound` (a lower bound on the approximate
- * distance of every non-candidate).  If merge_existing, cand_* hold the running state
- * (streaming over db shards).  Operands come from mmu_knn_tc_prepare. */
-int mmu_knn_tc_candidates(const void *q_hi, const void *q_lo, const float *q_sqnorm,
-                          int64_t n_query, int64_t n_query_padded,
-                          const void *db_hi, const void *db_lo, const float *db_sqnorm,
-                          int64_t n_db, int64_t n_db_padded, int dim_padded, int passes,
-                          int n_cand, int exclude_self, int64_t query_index_base,
-                          int64_t db_index_base, int merge_existing,
-                          int32_t *cand_idx, float *cand_d2, void *workspace, size_t workspace_bytes,
-                          mmu_stream_t stream);
-
-/* K2: rescore candidates with the canonical fp32 distance, select the k best by
- * (dist, index), and certify each row: row is certified iff every non-candidate is provably
- * farther than the k-th selected neighbour, i.e. sqrtf(cand_bound - eps_row) > dist_k with
- * eps_row = err_coef * (|q|^2 + max|y|^2).  uncertified_rows/n_uncertified (device) receive
- * the rows that must be recomputed with mmu_knn_exact_f32.  db rows are addressed by GLOBAL
- * index minus db_index_base. */
-int mmu_knn_rescore(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim,
-                    const int32_t *cand_idx, const float *cand_d2, int n_cand, int k,
-                    const float *q_sqnorm, float db_sqnorm_max, float err_coef,
-                    int64_t db_index_base, int32_t *out_idx, float *out_dist,
-                    int32_t *uncertified_rows, int32_t *n_uncertified, mmu_stream_t stream);
-
 /* ------------------------------------------------------------------------------------
  * K4  rho / sigma / membership weights   ref: model.py:33-61 (get_sigmas), :197-209
  * One warp per row.  rho = row minimum.  solver 0 = bisection (64 steps) of

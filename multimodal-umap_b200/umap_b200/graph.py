@@ -93,11 +93,16 @@ def knn_exact_simt(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: 
     return idx, dist
 
 
+def available_knn_methods():
+    """kNN engines compiled into the library ("tc" needs the mmu_knn_tc_* entry points)."""
+    return ("simt", "tc") if hasattr(lib(), "mmu_knn_tc_candidates") else ("simt",)
+
+
 def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, method: str | None = None):
     """Exact kNN of `query` rows in `db` (ref: model.py:81-195 role; semantics of
     oracle/knn_oracle.c).  method: "tc" (tcgen05 candidates + fp32 rescoring + certification),
     "simt" (exhaustive fp32 on CUDA cores) or None = env MMUMAP_KNN, default "tc"."""
-    method = method or os.environ.get("MMUMAP_KNN", "tc")
+    method = method or os.environ.get("MMUMAP_KNN", available_knn_methods()[-1])
     if k > native.MAX_K:
         raise ValueError(f"k_neighbors={k} exceeds the supported maximum {native.MAX_K}")
     if db.shape[0] - (1 if exclude_self else 0) < k:
