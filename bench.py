@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- UMAP fit benchmark of the B200 engine (and of the CPU reference arm).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path
+
+One "step" is one complete fit of the workload (default: BASELINE.json configs[1], the
+Flickr30k-shaped cross-modal fit: texts 158,915x768 + images 31,783x4096, k=15, 16-D, with the
+reference CLI's optimiser defaults main.py:13-21 -- 600 epochs, num_rep 8, lr 0.01, alpha 1,
+batch 256): exact kNN -> rho/sigma -> fuzzy union -> spectral init -> layout optimisation
+(UMAPMixture.fit, /root/reference/impl/model.py:483-508).  Data is synthetic.
+
+The JSON line printed by rank 0:
+  metric/value   umap_fit_seconds with the inputs already resident in HBM (device timed, CUDA
+                 events, max over ranks), lower is better;
+  e2e            the same fit through the reference-facing API impl.util.train() with HOST
+                 (pinned) inputs and the embeddings read back to the host, wall-clocked between
+                 synchronisations;
+  roofline       the dominant kernel (exact kNN contraction) against the measured bf16 peak;
+  stages         per-stage device times, kNN TFLOP/s, optimiser edge-updates/s and GB/s;
+  cpu_baseline   the CPU port (oracle/) on a bounded sample, extrapolated to the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multimodal-umap_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2": dict(desc="Flickr30k-shaped cross-modal fit: texts 158915x768 + images 31783x4096, k=15, 16-D",
+               mods=[("texts", 158915, 768, "bert"), ("images", 31783, 4096, "vae")],
+               k=15, out_dim=16, epochs=600),
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case)
+    "c1": dict(desc="2000x64 Gaussian blobs, k=15, 2-D, 200 epochs", mods=[("blobs", 2000, 64, "blobs")],
+               k=15, out_dim=2, epochs=200),
+    # reduced C2 for functional checks of this script (NOT a benchmark configuration)
+    "c2-tiny": dict(desc="C2 generators at 1/16 rows (script self-test only)",
+                    mods=[("texts", 9932, 768, "bert"), ("images", 1986, 4096, "vae")], k=15, out_dim=16, epochs=50),
+}
+OPT = dict(min_dist=0.1, num_rep=8, lr=0.01, alpha=1.0, batch_size=256)      # reference main.py:15-21
+
+
+# --------------------------------------------------------------------------- synthetic data
+def make_data(workload: dict, seed: int = 0) -> dict:
+    """SURVEY.md 8(d) generators on the CPU generator (identical for both arms)."""
+    gen = torch.Generator().manual_seed(seed)
+    n_clusters = 64
+    n_img = min(n for (_, n, _, _) in workload["mods"])
+    out = {}
+    for name, n, d, kind in workload["mods"]:
+        cluster = (torch.arange(n) % n_img) % n_clusters      # caption c <-> image c mod N_img
+        if kind == "vae":       # SD-VAE latent_dist.mean scale: centre N(0,2^2) + N(0,4^2) noise
+            centres = torch.randn((n_clusters, d), generator=gen) * 2.0
+            x = centres[cluster] + torch.randn((n, d), generator=gen) * 4.0
+        elif kind == "bert":    # BERT pooler_output: tanh-bounded
+            centres = torch.randn((n_clusters, d), generator=gen)
+            x = torch.tanh(centres[cluster] + torch.randn((n, d), generator=gen) * 0.5)
+        else:                   # C1: centres N(0,5^2), points = centre + N(0,1)
+            centres = torch.randn((10, d), generator=gen) * 5.0
+            x = centres[torch.arange(n) % 10] + torch.randn((n, d), generator=gen)
+        out[name] = x.contiguous()
+    return out
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU port (oracle)
+def cpu_fit_sample(data: dict, workload: dict, threads: int, knn_rows: int | None = None) -> dict:
+    """Times the CPU port of the reference path (oracle/) on a bounded sample of `workload` and
+    extrapolates to fit seconds.  The reference's own kNN (NN-descent, model.py:81-195) does not
+    complete at C2 scale, so the kNN leg is the exhaustive restatement the GPU
+    path is held bit-exact to, timed on `knn_rows` query rows per modality against the FULL
+    database with all host threads and scaled by N/knn_rows; sigma/union run at full size on the
+    sampled rows' statistics (random k-regular stand-in graph for the rows not searched); the
+    optimiser leg times ONE epoch of the restated _train (model.py:396-481) at full size and
+    scales by the epoch count.  Spectral init: scipy lobpcg on the stand-in graph."""
+    from oracle import umap_oracle as orc
+    import warnings
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(threads)
+    k, d_out, epochs = workload["k"], workload["out_dim"], workload["epochs"]
+    rng = np.random.default_rng(0)
+    t_knn = t_knn_port = t_sigma = t_union = t_spec = 0.0
+    flops_port = 0.0
+    graphs, inits = [], []
+    knn_rows = knn_rows or max(8, 2 * threads)
+    flops = 0.0
+    for name, x in data.items():
+        xn = x.numpy()
+        n = xn.shape[0]
+        q = min(knn_rows, n)
+        t0 = time.perf_counter()
+        idx_s, dist_s = orc.knn_exact(xn[:q], xn, k, True, nthreads=threads)
+        dt = time.perf_counter() - t0
+        t_knn_port += dt * n / q
+        flops_port += 2.0 * q * n * xn.shape[1] / dt
+        # the same search as a blocked dense contraction on all host cores (torch.cdist + topk):
+        # the fastest CPU statement of the kNN leg, used for the extrapolated fit time
+        qc = min(n, 2048)
+        t0 = time.perf_counter()
+        torch.cdist(x[:qc], x, compute_mode="use_mm_for_euclid_dist").topk(k + 1, dim=1, largest=False)
+        dt = time.perf_counter() - t0
+        t_knn += dt * n / qc
+        flops += 2.0 * qc * n * xn.shape[1] / dt
+        # stand-in graph for the rows not searched: random neighbours, distances resampled from the searched rows
+        idx = rng.integers(0, n, (n, k)).astype(np.int32)
+        dist = np.sort(rng.choice(dist_s.reshape(-1), (n, k)), axis=1).astype(np.float32)
+        idx[:q], dist[:q] = idx_s, dist_s
+        t0 = time.perf_counter()
+        sig = orc.sigmas_bisect(dist)
+        w = orc.membership_weights(dist, sig)
+        ci, cw = orc.coalesce_rows(idx, w)
+        t_sigma += time.perf_counter() - t0
+        rows = np.repeat(np.arange(n, dtype=np.int64), k)
+        # de-duplicate the stand-in rows so the COO is coalesced like the reference's
+        key = rows * n + ci.reshape(-1)
+        _, first = np.unique(key, return_index=True)
+        rows, cols, vals = rows[first], ci.reshape(-1)[first].astype(np.int64), cw.reshape(-1)[first]
+        t0 = time.perf_counter()
+        ur, uc, uv = orc.fuzzy_union(rows, cols, vals, n)
+        t_union += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        s = sp.coo_matrix((uv.astype(np.float32), (ur, uc)), shape=(n, n)).tocsr()
+        deg = np.maximum(np.asarray(s.sum(axis=1)).ravel(), 1e-6)
+        dm = sp.diags((deg ** -0.5).astype(np.float32))
+        lap = sp.identity(n, dtype=np.float32) * np.float32(1.0 + 1e-6) - dm @ s @ dm
+        x0 = rng.standard_normal((n, d_out + 1)).astype(np.float32)
+        try:
+            _, vecs = spla.lobpcg(lap, x0, largest=False, tol=3.5e-4, maxiter=40)
+        except Exception:
+            vecs = x0
+        t_spec += time.perf_counter() - t0
+        graphs.append((ur, uc, uv))
+        inits.append(np.ascontiguousarray(vecs[:, 1:d_out + 1] if vecs.shape[1] > d_out else vecs[:, :d_out],
+                                          dtype=np.float32))
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    kept_rec = []
+    orc.train_oracle(inits, graphs, 1, OPT["num_rep"], OPT["lr"], OPT["alpha"], OPT["batch_size"], 1.577, 0.8951,
+                     mode="fit", infonce=orc.infonce_grad_vec, record=kept_rec)
+    t_epoch = time.perf_counter() - t0
+    kept = sum(float(g[2].sum()) for g in graphs)          # E[kept] = sum of weights (Bernoulli(w), model.py:432)
+    total = t_knn + t_sigma + t_union + t_spec + t_epoch * epochs
+    return {
+        "fit_seconds": total,
+        "parts_s": {"knn_extrapolated": t_knn, "knn_exact_port_extrapolated": t_knn_port, "sigma": t_sigma, "union": t_union, "spectral_40it": t_spec,
+                    "one_epoch": t_epoch, "optimise_extrapolated": t_epoch * epochs},
+        "knn_tflops": flops / len(data) / 1e12,
+        "knn_exact_port_tflops": flops_port / len(data) / 1e12,
+        "edge_updates_per_s": kept * (1 + OPT["num_rep"]) / t_epoch,
+        "sample": (f"kNN as torch.cdist+topk on 2048 query rows/modality vs full db (x N/2048; the bit-exact C port "
+                   f"on {knn_rows} rows is reported beside it); sigma+union+scipy-lobpcg(40 it) "
+                   f"full size on a stand-in graph; 1 of {epochs} optimiser epochs (x{epochs})"),
+    }
+
+
+# --------------------------------------------------------------------------- this engine
+def run_b200(args, workload, data):
+    import torch.distributed as dist
+    from umap_b200 import native, profiler
+    import importlib
+    model_mod = importlib.import_module("impl.model")
+    util_mod = importlib.import_module("impl.util")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    dev = torch.device("cuda", local)
+    cfg = util_mod.Config(k_neighbors=workload["k"], out_dim=workload["out_dim"], min_dist=OPT["min_dist"],
+                          train_epochs=workload["epochs"], num_rep=OPT["num_rep"], lr=OPT["lr"], alpha=OPT["alpha"],
+                          batch_size=OPT["batch_size"], test_epochs=120)
+    host = {k: v.pin_memory() for k, v in data.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def fit_resident():
+        torch.manual_seed(1234)
+        return util_mod.train(resident, cfg)
+
+    def fit_e2e():
+        torch.manual_seed(1234)
+        model = util_mod.train(host, cfg)                   # H2D copies happen inside (model.py:496,634)
+        return [e.detach().cpu() for e in model.embeds]     # D2H read of the result
+
+    for _ in range(args.warmup):
+        fit_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = native.lib().mmu_launch_count()
+    profiler.enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    model = None
+    for _ in range(args.steps):
+        model = fit_resident()
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = native.lib().mmu_launch_count() - launches0
+    stages = profiler.summarize(profiler.collect())
+    profiler.enable(False)
+    kept = model.last_optimizer.kept_last_epoch()
+    nnz = [int(model.last_optimizer.mods[i].graph.nnz) for i in range(len(model.last_optimizer.mods))]
+    rows = [int(m.count) for m in model.last_optimizer.mods]
+
+    # end to end through the reference-facing API, host buffers in, host result out
+    fit_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fit_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    steps = args.steps
+    st = {k: dict(v, ms=v["ms"] / steps) for k, v in stages.items()}
+    knn = stages.get("knn", {"ms": 0.0, "calls": 1, "flops": 0.0})
+    knn_tflops = knn.get("flops", 0.0) / (knn["ms"] * 1e-3) / 1e12 if knn["ms"] > 0 else 0.0
+    # a kNN stage timed inside a seconds-long step: sustained peak
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
+    d = workload["out_dim"]
+    epochs = workload["epochs"]
+    opt_ms = stages.get("optimise", {"ms": 0.0})["ms"] / steps
+    # SURVEY.md 8(d) canonical per-epoch bytes, fit mode, device RNG, int32 COO
+    bytes_epoch = sum(12 * z for z in nnz) + kept * (2 + OPT["num_rep"]) * d * 4 * 2 + sum(28 * r * d for r in rows)
+    edge_updates = kept * (1 + OPT["num_rep"])
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "umap_fit_seconds", "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": workload["desc"], "epochs": epochs, **OPT,
+                   "knn_method": os.environ.get("MMUMAP_KNN", "default"),
+                   "sample_stream": os.environ.get("MMUMAP_SAMPLE_STREAM", "device"),
+                   "l2": "inputs (1.0 GB) exceed the 126 MB L2; every step re-reads them from HBM",
+                   "parallelism": f"kNN query-row blocks x{world}, optimiser edge shards x{world}" if world > 1 else "1 GPU"},
+        "e2e": {"value": e2e_s, "unit": "s",
+                "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())),
+                "d2h_bytes_per_step": int(sum(r * d * 4 for r in rows))},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "exact kNN contraction", "bound": "tensor", "achieved": knn_tflops, "peak": tensor_peak,
+                     "unit": "TFLOP/s", "frac": knn_tflops / tensor_peak, "traffic": None, "peak_source": peak_src,
+                     "share_of_step": knn["ms"] / total_ms if total_ms else None},
+        "stages": {
+            "ms": {k: round(v["ms"], 3) for k, v in st.items()},
+            "knn_tflops": knn_tflops,
+            "sgd_edge_updates_per_s": edge_updates * epochs / (opt_ms * 1e-3) if opt_ms else None,
+            "sgd_gbs": bytes_epoch * epochs / (opt_ms * 1e-3) / 1e9 if opt_ms else None,
+            "sgd_hbm_frac": (bytes_epoch * epochs / (opt_ms * 1e-3) / 1e9) / hbm_peak if opt_ms else None,
+            "kept_edges_last_epoch": kept, "union_nnz": nnz,
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = cpu_fit_sample(data, workload, threads)
+        line["cpu_baseline"] = {"value": cb["fit_seconds"], "unit": "s", "cores": threads, "kind": "port",
+                                "sample": cb["sample"], "parts_s": cb["parts_s"], "knn_tflops": cb["knn_tflops"],
+                                "edge_updates_per_s": cb["edge_updates_per_s"]}
+    return line
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, workload, data):
+    """The reference is pure Python/PyTorch (nothing to compile into oracle/_ref), its kNN does
+    not complete at this size and it cannot travel to the GPU box; the arm therefore times the
+    CPU port of its path (oracle/), all host threads, each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup):
+        cpu_fit_sample(data, workload, threads, knn_rows=max(2, threads // 4))
+    t0 = time.perf_counter()
+    cb = None
+    for _ in range(args.steps):
+        cb = cpu_fit_sample(data, workload, threads)
+        vals.append(cb["fit_seconds"])
+    wall = time.perf_counter() - t0
+    v = statistics.mean(vals)
+    return {
+        "impl": "reference", "metric": "umap_fit_seconds", "value": v, "unit": "s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": workload["desc"], "epochs": workload["epochs"], **OPT},
+        "cpu_baseline": {"value": v, "unit": "s", "cores": threads, "kind": "port", "sample": cb["sample"],
+                         "parts_s": cb["parts_s"], "knn_tflops": cb["knn_tflops"],
+                         "edge_updates_per_s": cb["edge_updates_per_s"], "sample_wall_s": wall / max(args.steps, 1)},
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--epochs", type=int, default=None, help="override the workload's epoch count (not a benchmark configuration)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    workload = dict(WORKLOADS[args.workload])
+    if args.epochs is not None:
+        workload["epochs"] = args.epochs
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        args.warmup = min(args.warmup, 1)
+    data = make_data(workload)
+    line = run_reference(args, workload, data) if args.impl == "reference" else run_b200(args, workload, data)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,9 @@ typedef void *mmu_stream_t;
 
 int mmu_abi_version(void);
 const char *mmu_last_error(void);
+/* Number of kernels of this library launched by the process so far (every launch site counts
+ * itself); bench.py reports the difference over its timed region as "gpu_launches". */
+uint64_t mmu_launch_count(void);
 /* Device properties the host uses to size persistent grids. Synchronous. */
 int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
 
@@ -125,7 +128,7 @@ int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, in
 int mmu_opt_state_init(uint32_t *state, mmu_stream_t stream);
 /* epoch += 1, step += 1, recompute Adam's step_size = lr/(1-beta1^step) and
  * bc2_sqrt = sqrt(1-beta2^step) in double precision. */
-int mmu_opt_state_advance(uint32_t *state, float lr, float beta1, float beta2, mmu_stream_t stream);
+int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, double beta2, mmu_stream_t stream);
 
 /* K7a (device sample stream): Bernoulli(w) keep per edge (ref: model.py:432) with a
  * counter-based Philox4x32-10 stream keyed by (seed, state->epoch, edge position).  Writes the
@@ -166,9 +169,12 @@ int mmu_infonce(const float *e0, const float *e1, int64_t num, int dim, const in
 
 /* K9: fused Adam update over a dense table (torch.optim.Adam single-tensor semantics,
  * eps=1e-8 style denominator sqrt(v)/bc2_sqrt + eps), reading step_size / bc2_sqrt from
- * `state`; zero_grad != 0 also clears g.            ref: model.py:403,474-476 */
-int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, float beta1, float beta2,
-                  float eps, const uint32_t *state, int zero_grad, mmu_stream_t stream);
+ * `state`; zero_grad != 0 also clears g.  Hyper-parameters are doubles because torch forms
+ * 1-beta in double before rounding to fp32; every fp32 operation is rounded separately (no
+ * fma contraction) so the update equals torch's CPU result bit for bit.
+ *                                                  ref: model.py:403,474-476 */
+int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, double beta1, double beta2,
+                  double eps, const uint32_t *state, int zero_grad, mmu_stream_t stream);
 
 #ifdef __cplusplus
 }

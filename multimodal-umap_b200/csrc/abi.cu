@@ -14,6 +14,9 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 int sm_count() {
     static int cached = -1;
     if (cached < 0) {
@@ -34,6 +37,8 @@ int sm_count() {
 extern "C" int mmu_abi_version(void) { return MMU_ABI_VERSION; }
 
 extern "C" const char *mmu_last_error(void) { return mmu::g_err; }
+
+extern "C" uint64_t mmu_launch_count(void) { return __atomic_load_n(&mmu::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes) {
     using namespace mmu;

@@ -28,8 +28,12 @@ void set_error(const char *fmt, ...);
         }                                                                                \
     } while (0)
 
-#define MMU_LAUNCH_CHECK()                                                               \
+void count_launch(int n);   // n of OUR kernels were launched (mmu_launch_count)
+
+#define MMU_LAUNCH_CHECK() MMU_LAUNCH_CHECK_N(1)
+#define MMU_LAUNCH_CHECK_N(n_launched)                                                   \
     do {                                                                                 \
+        mmu::count_launch(n_launched);                                                   \
         cudaError_t _e = cudaGetLastError();                                             \
         if (_e != cudaSuccess) {                                                         \
             mmu::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \

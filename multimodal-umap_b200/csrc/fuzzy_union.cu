@@ -102,7 +102,7 @@ static int exclusive_scan(const TI *in, int64_t n, TO *out, TO *partial, int wri
     scan_tile_sums<TI, TO><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, partial);
     scan_partials<TO><<<1, 1024, 0, st>>>(partial, tiles);
     scan_apply<TI, TO><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, partial, out, write_total);
-    MMU_LAUNCH_CHECK();
+    MMU_LAUNCH_CHECK_N(3);
     return MMU_OK;
 }
 
@@ -359,7 +359,7 @@ extern "C" int mmu_fuzzy_union(const int32_t *col, const float *w, int64_t n, in
         else
             radix_scatter_kernel<false><<<rs_blocks, RS_WARPS * 32, rs_smem, st>>>(
                 kin, sin, win, p.items, k, shift, p.bins, p.n_tiles, hist, key[cur], src[cur], wv[cur]);
-        MMU_LAUNCH_CHECK();
+        MMU_LAUNCH_CHECK_N(2);
         kin = key[cur]; sin = src[cur]; win = wv[cur];
         cur ^= 1;
     }
@@ -378,6 +378,6 @@ extern "C" int mmu_fuzzy_union(const int32_t *col, const float *w, int64_t n, in
     rc = exclusive_scan<uint32_t, int64_t>(cnt, n, out_rowptr, partial64, 1, st);
     if (rc) return rc;
     union_write_kernel<<<wblocks, 256, 0, st>>>(col, w, n, k, tptr, tsrc, tw, out_rowptr, out_row, out_col, out_val);
-    MMU_LAUNCH_CHECK();
+    MMU_LAUNCH_CHECK_N(3);
     return MMU_OK;
 }

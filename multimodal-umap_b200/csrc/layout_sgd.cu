@@ -19,13 +19,13 @@ __global__ void opt_state_init_kernel(OptState *s) {
     s->epoch = 0; s->step = 0; s->step_size = 0.f; s->bc2_sqrt = 1.f;
     for (int i = 0; i < 4; ++i) s->reserved[i] = 0;
 }
-__global__ void opt_state_advance_kernel(OptState *s, float lr, float beta1, float beta2) {
+__global__ void opt_state_advance_kernel(OptState *s, double lr, double beta1, double beta2) {
     uint32_t step = s->step + 1;
     s->step = step;
     s->epoch = s->epoch + 1;
-    double bc1 = 1.0 - pow((double)beta1, (double)step);
-    double bc2 = 1.0 - pow((double)beta2, (double)step);
-    s->step_size = (float)((double)lr / bc1);
+    double bc1 = 1.0 - pow(beta1, (double)step);
+    double bc2 = 1.0 - pow(beta2, (double)step);
+    s->step_size = (float)(lr / bc1);
     s->bc2_sqrt = (float)sqrt(bc2);
 }
 
@@ -371,19 +371,21 @@ infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64
 // ------------------------------------------------------------------ K9: Adam
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-            int64_t n, float beta1, float beta2, float eps, const OptState *__restrict__ st, int zero_grad) {
-    const float step_size = st->step_size, bc2_sqrt = st->bc2_sqrt;
-    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+            int64_t n, float beta2, float omb1, float omb2, float eps, const OptState *__restrict__ st,
+            int zero_grad) {
+    // torch.optim.Adam (single-tensor path) operation by operation, one rounding each: no fma
+    // contraction, so that the result equals the CPU reference bit for bit.
+    const float neg_step = -st->step_size, bc2_sqrt = st->bc2_sqrt;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float gg = g[i];
         float mm = m[i];
         float vv = v[i];
-        mm = mm + omb1 * (gg - mm);                     // exp_avg.lerp_(grad, 1-beta1)
-        vv = vv * beta2 + (omb2 * gg) * gg;             // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        float denom = sqrtf(vv) / bc2_sqrt + eps;
-        p[i] = p[i] + (-step_size * mm) / denom;        // addcdiv_(exp_avg, denom, value=-step_size)
+        mm = __fadd_rn(mm, __fmul_rn(omb1, __fsub_rn(gg, mm)));                        // exp_avg.lerp_(grad, 1-beta1)
+        vv = __fadd_rn(__fmul_rn(vv, beta2), __fmul_rn(__fmul_rn(omb2, gg), gg));      // mul_(beta2).addcmul_(g, g, 1-beta2)
+        float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+        p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(neg_step, mm), denom));             // addcdiv_(exp_avg, denom, -step_size)
         m[i] = mm;
         v[i] = vv;
         if (zero_grad) g[i] = 0.f;
@@ -407,7 +409,7 @@ extern "C" int mmu_opt_state_init(uint32_t *state, mmu_stream_t stream) {
     return MMU_OK;
 }
 
-extern "C" int mmu_opt_state_advance(uint32_t *state, float lr, float beta1, float beta2, mmu_stream_t stream) {
+extern "C" int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, double beta2, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(state, "mmu_opt_state_advance: null pointer");
     opt_state_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<OptState *>(state), lr, beta1, beta2);
@@ -489,7 +491,7 @@ extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int di
     return MMU_OK;
 }
 
-extern "C" int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, float beta1, float beta2, float eps,
+extern "C" int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, double beta1, double beta2, double eps,
                              const uint32_t *state, int zero_grad, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(p && g && m && v && state, "mmu_adam_step: null pointer");
@@ -497,7 +499,9 @@ extern "C" int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, 
     int64_t want = (n + 255) / 256;
     unsigned cap = persistent_blocks(256, 16);
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
-    adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+    // 1-beta is formed in double and rounded once, as torch does with its Python-float betas
+    adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, (float)beta2, (float)(1.0 - beta1),
+                                                       (float)(1.0 - beta2), (float)eps,
                                                        reinterpret_cast<const OptState *>(state), zero_grad);
     MMU_LAUNCH_CHECK();
     return MMU_OK;

@@ -24,7 +24,7 @@ import weakref
 import torch
 
 from umap_b200 import graph as G
-from umap_b200 import native
+from umap_b200 import native, profiler
 from umap_b200.layout import LayoutOptimizer
 from umap_b200.spectral import spectral_init
 
@@ -83,7 +83,8 @@ class UMAPEncoder:
         q = inputs if query is None else query
         idx, dist = G.knn_graph(q, inputs, self.k_neighbors, exclude_self=ref_data is None, method=self.knn_method)
         if mode != "invert":
-            col, w, sigma, rho = G.smooth_knn(idx, dist, self.sigma_solver)
+            with profiler.stage("smooth_knn", bytes=float(idx.shape[0]) * (16 * self.k_neighbors + 8)):
+                col, w, sigma, rho = G.smooth_knn(idx, dist, self.sigma_solver)
             if mode == "fit":
                 self.sigmas, self.rhos = sigma, rho                      # model.py:202-204
         else:
@@ -115,9 +116,11 @@ class UMAPEncoder:
         graph = self.fuzzy_knn_graph(input, mode, query, ref_data, num_iters=10, a=a, b=b)
         if mode == "fit":
             g = _as_graph(graph)
-            sym = G.fuzzy_union(g.col2d, g.w2d)                          # model.py:271
+            with profiler.stage("fuzzy_union"):
+                sym = G.fuzzy_union(g.col2d, g.w2d)                      # model.py:271
             graph = _coo(sym)
-            embed = self.embed_all(graph)
+            with profiler.stage("spectral_init"):
+                embed = self.embed_all(graph)
         elif mode == "transform":
             embed = self.embed_query(ref_embeds, graph)
         else:
@@ -161,7 +164,8 @@ class UMAPMixture:
         opt = LayoutOptimizer(embeds, [_as_graph(g) for g in graphs], self.a, self.b, num_rep, lr, alpha,
                               batch_size, mode=mode, refs=refs,
                               sample_stream=getattr(self, "sample_stream", None))
-        out = opt.run(epochs)
+        with profiler.stage("optimise", epochs=epochs):
+            out = opt.run(epochs)
         self.last_optimizer = opt
         return [e.requires_grad_(True) for e in out]                     # leaves, as model.py:397,481
 

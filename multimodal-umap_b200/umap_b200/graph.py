@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 import torch
 
-from . import native
+from . import native, profiler
 from .native import check, lib, ptr, stream
 
 
@@ -107,11 +107,14 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         raise ValueError(f"k_neighbors={k} exceeds the supported maximum {native.MAX_K}")
     if db.shape[0] - (1 if exclude_self else 0) < k:
         raise ValueError(f"need more than k={k} candidate points per row, got {db.shape[0]}")
+    flops = 2.0 * query.shape[0] * db.shape[0] * db.shape[1]
     if method == "simt":
-        return knn_exact_simt(query, db, k, exclude_self)
+        with profiler.stage("knn", flops=flops, kernel="knn_exact_f32_kernel"):
+            return knn_exact_simt(query, db, k, exclude_self)
     if method == "tc":
         from .knn_tc import knn_tc
-        return knn_tc(query, db, k, exclude_self)
+        with profiler.stage("knn", flops=flops, kernel="knn_tc"):
+            return knn_tc(query, db, k, exclude_self)
     raise ValueError(f"unknown kNN method {method!r}")
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 import torch
 
@@ -28,6 +28,7 @@ class NativeError(RuntimeError):
 _SIGNATURES = {
     "mmu_abi_version": (c_int, []),
     "mmu_last_error": (ctypes.c_char_p, []),
+    "mmu_launch_count": (c_uint64, []),
     "mmu_device_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_exact_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
                                   c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -41,7 +42,7 @@ _SIGNATURES = {
     "mmu_embed_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_spmm_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
-    "mmu_opt_state_advance": (c_int, [c_void_p, c_float, c_float, c_float, c_void_p]),
+    "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
     "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -49,7 +50,7 @@ _SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "mmu_infonce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                             c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
-    "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_void_p,
+    "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p,
                               c_int, c_void_p]),
 }
 

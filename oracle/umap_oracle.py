@@ -299,6 +299,49 @@ def infonce_grad(e0: np.ndarray, e1: np.ndarray, perm: np.ndarray, negs: np.ndar
     return loss, g0, g1
 
 
+def infonce_grad_vec(e0: np.ndarray, e1: np.ndarray, perm: np.ndarray, negs: np.ndarray,
+                     temperature: float = 0.5, chunk: int = 1000):
+    """Vectorised numpy form of infonce_grad (same closed form of model.py:364-394, fp64);
+    used where the per-anchor Python loop is too slow (bench.py's CPU baseline).  Pinned to the
+    loop version by tests/test_oracle_golden.py."""
+    num = perm.shape[0]
+    g0 = np.zeros(e0.shape, dtype=np.float64)
+    g1 = np.zeros(e1.shape, dtype=np.float64)
+    if num == 0:
+        return 0.0, g0, g1
+    n_chunks = (num + chunk - 1) // chunk
+    t = np.arange(num)
+    clen = np.minimum(chunk, num - (t // chunk) * chunk)
+    wgt = 1.0 / (clen * n_chunks)                                    # [num]
+    i = perm.astype(np.int64)
+    cand = np.concatenate([i[:, None], negs.astype(np.int64)], axis=1)          # [num, M]
+    valid = np.concatenate([np.ones((num, 1), bool), negs != i[:, None]], axis=1)
+    a = e0[i].astype(np.float64)
+    an = np.maximum(np.linalg.norm(a, axis=1), 1e-12)
+    u = a / an[:, None]
+    ev = e1[cand].astype(np.float64)                                  # [num, M, d]
+    en = np.maximum(np.linalg.norm(ev, axis=2), 1e-12)
+    v = ev / en[:, :, None]
+    cs = np.einsum("nd,nmd->nm", u, v)
+    logits = np.where(valid, cs / temperature, -np.inf)
+    mx = logits.max(axis=1, keepdims=True)
+    ex = np.exp(logits - mx)
+    den = ex.sum(axis=1, keepdims=True)
+    pi = ex / den
+    loss = float((wgt * -(logits[:, 0] - mx[:, 0] - np.log(den[:, 0]))).sum())
+    cm = pi.copy()
+    cm[:, 0] -= 1.0
+    cm = np.where(valid, cm, 0.0)
+    acc = np.einsum("nm,nmd->nd", cm, v)
+    ga = acc - u * (u * acc).sum(axis=1, keepdims=True)
+    np.add.at(g0, i, (wgt / (temperature * an))[:, None] * ga)
+    gv = cm[:, :, None] * u[:, None, :]
+    gv = gv - v * (v * gv).sum(axis=2, keepdims=True)
+    gv = gv * (wgt[:, None] / (temperature * en))[:, :, None]
+    np.add.at(g1, cand.reshape(-1), gv.reshape(-1, e1.shape[1]))
+    return loss, g0, g1
+
+
 def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
     """torch.optim.Adam single-tensor update (model.py:403,476), fp32."""
     p = p.astype(np.float32)
@@ -316,7 +359,7 @@ def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8
 
 # ------------------------------------------------------------- _train restated
 def train_oracle(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, a, b, mode="fit",
-                 refs=None, record=None):
+                 refs=None, record=None, infonce=None):
     """Restatement of UMAPMixture._train (model.py:396-481) for modes "fit"/"transform",
     drawing from torch's global CPU generator in the reference's call order
     (SURVEY.md section 3.3).  `graphs` = list of (rows, cols, vals) coalesced COO arrays;
@@ -369,7 +412,7 @@ def train_oracle(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, a, b, m
                             en = min(st + 1000, num)
                             negs.append(torch.randint(0, num, (en - st, 9)).numpy())
                         negs = np.concatenate(negs, axis=0) if negs else np.zeros((0, 9), dtype=np.int64)
-                        l, g0, g1 = infonce_grad(ys[s], ys[t], perm, negs)
+                        l, g0, g1 = (infonce or infonce_grad)(ys[s], ys[t], perm, negs)
                         # total loss carries alpha*(L_ij+L_ji): model.py:467-472
                         grads[s] += alpha * g0
                         grads[t] += alpha * g1

@@ -138,6 +138,20 @@ def test_infonce_matches_reference_autograd(golden_dir):
     assert np.allclose(g1, g["infonce_g1"], rtol=1e-4, atol=1e-8)
 
 
+def test_infonce_vectorised_equals_loop_version():
+    rng = np.random.default_rng(4)
+    e0 = rng.standard_normal((2300, 6)).astype(np.float32)
+    e1 = rng.standard_normal((2500, 6)).astype(np.float32)
+    num = 2300
+    perm = rng.permutation(num)
+    negs = rng.integers(0, num, (num, 9))
+    negs[::7, 3] = perm[::7]                      # masked negatives (model.py:386)
+    l0, a0, b0 = orc.infonce_grad(e0, e1, perm, negs)
+    l1, a1, b1 = orc.infonce_grad_vec(e0, e1, perm, negs)
+    assert abs(l0 - l1) < 1e-12
+    assert np.allclose(a0, a1, rtol=1e-10, atol=1e-16) and np.allclose(b0, b1, rtol=1e-10, atol=1e-16)
+
+
 def _graphs(g, n):
     return [(g[f"rows{m}"], g[f"cols{m}"], g[f"vals{m}"]) for m in range(n)]
 
