@@ -70,6 +70,25 @@ int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_
                       int64_t query_index_base, int64_t db_index_base, int merge_existing,
                       int32_t *out_idx, float *out_dist, mmu_stream_t stream);
 
+/* Tensor-core path (tcgen05.mma kind::f16, TMEM accumulators, TMA operand staging): candidates
+ * are generated from a centred, power-of-two scaled fp16 copy of the data with a fused per-row
+ * top-64 selection in the epilogue; each row is then CERTIFIED from a rigorous bound on the fp16
+ * error (no point outside its candidate list can be among the k nearest) and the surviving
+ * candidates are rescored with the canonical fp32 distance above, so certified rows equal
+ * mmu_knn_exact_f32 bit for bit.  Rows that cannot be certified (exact ties, degenerate data) are
+ * NOT written; their indices are appended to fallback_rows and counted in stats[0] -- the caller
+ * runs mmu_knn_exact_f32 with query_ids = fallback_rows on them.
+ *   stats[0] rows left for the exhaustive kernel, stats[1] candidates rescored, stats[2] rows
+ *   certified, stats[3] reserved (4 x int32, zeroed by the call); fallback_rows: [n_query].
+ * query_is_db != 0 (fit mode): query and db are the same array and share one fp16 copy.
+ * out_idx holds db row numbers; exclude_self drops the pair j == query_index_base + q. */
+#define MMU_KNN_TC_MAX_K 32
+size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db);
+int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
+               int exclude_self, int64_t query_index_base, int query_is_db, void *workspace,
+               size_t workspace_bytes, int32_t *out_idx, float *out_dist, int32_t *stats,
+               int32_t *fallback_rows, mmu_stream_t stream);
+
 /* K3: merge two sorted per-row lists (e.g. from two db shards) into one sorted top-k. */
 int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_b,
                   const float *dist_b, int64_t n_rows, int k, int32_t *out_idx, float *out_dist,

@@ -1,0 +1,736 @@
+// knn_tc.cu -- K1/K2: exact kNN through the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces the reference's candidate search and per-row top-k
+// (/root/reference/impl/model.py:81-195; distance :109,:163; selection :181-193; self exclusion
+// :88,:166).  Three launches, all on the caller's stream:
+//
+//   prep       X (fp32) -> centred, power-of-two scaled fp16 copy X16 [rows_pad x D_pad] plus the
+//              fp32 squared norms of the centred/scaled rows (translation and scaling leave the
+//              ranking unchanged; centring minimises |x||y|, the quantity the error bound uses).
+//   candidates dense contraction S~[q][j] = |Y_j|^2 - 2 X_q.Y_j on tcgen05.mma (kind::f16, fp32
+//              accumulators in TMEM, operands staged by TMA with the 128-byte swizzle, a 3/4-stage
+//              mbarrier pipeline, two TMEM accumulator buffers so that the epilogue of tile i
+//              overlaps the MMAs of tile i+1).  The epilogue is a fused per-row top-K' selection:
+//              one thread per TMEM lane (= query row) keeps its K' best approximate scores in a
+//              max-heap in shared memory (slot-major, so every access is bank-conflict free) and
+//              filters each accumulator value with ONE compare against the heap root.
+//   rescore    per query row (one warp): certify, from the approximate scores alone, that no point
+//              outside the candidate list can be among the k nearest -- every non-candidate has
+//              S~ >= tau (the list's largest score) and |S~ - S| <= eps, a rigorous bound on the fp16
+//              rounding + accumulation error -- then evaluate the reference's own fp32 distance
+//              expression in the canonical order of oracle/knn_oracle.c for the few candidates
+//              that can still reach the top k and rank them by (distance, index).  Rows that
+//              cannot be certified (ties, degenerate data) are listed for the exhaustive fp32
+//              kernel (mmu_knn_exact_f32), so the result is bit-exact by construction.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace mmu {
+
+constexpr int TC_BM = 128;        // query rows per CTA (= TMEM lanes)
+constexpr int TC_BN = 256;        // db rows per tile (= UMMA N, TMEM columns per accumulator)
+constexpr int TC_BK = 64;         // fp16 elements per k-block: 128 bytes = one swizzle span
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int TC_KP = 64;         // candidates kept per row and db split
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8;
+constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES + 256;
+constexpr int RS_PMAX = 128;      // most candidates rescored per row
+#define F_INF __int_as_float(0x7f800000)
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: 8-row groups of 1024 bytes (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D fp32 (bits 4-5 = 1), A/B fp16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+// ------------------------------------------------------------------ prep
+// column sums (deterministic two-level reduction) and the largest |x|
+__global__ void __launch_bounds__(256)
+tc_colsum_kernel(const float *__restrict__ x, int64_t n, int dim, int rows_per_block, float *__restrict__ partial,
+                 uint32_t *__restrict__ maxabs_bits) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(n, r0 + rows_per_block);
+    float mx = 0.f;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        float s = 0.f;
+        for (int64_t r = r0; r < r1; ++r) {
+            float v = x[r * dim + c];
+            s += v;
+            mx = fmaxf(mx, fabsf(v));
+        }
+        partial[(int64_t)blockIdx.x * dim + c] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxabs_bits, __float_as_uint(mx));
+}
+
+// prm[0] = scale (power of two), prm[1] = largest |Y|^2 (bits, atomicMax), prm[2] = largest |x| bits
+__global__ void tc_finish_stats_kernel(const float *__restrict__ partial, int n_blocks, int dim, int64_t n,
+                                       float *__restrict__ mean, uint32_t *__restrict__ prm, int center) {
+    __shared__ float s_mx[32];
+    float mu_max = 0.f;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)b * dim + c];
+        float mu = center ? s / (float)n : 0.f;
+        mean[c] = mu;
+        mu_max = fmaxf(mu_max, fabsf(mu));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mu_max = fmaxf(mu_max, __shfl_xor_sync(0xffffffffu, mu_max, o));
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mu_max;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_mx[w]);
+        float bound = __uint_as_float(prm[2]) + m;            // >= max |x - mean|
+        int e = 0;
+        if (bound > 0.f && bound < F_INF) {
+            (void)frexpf(bound, &e);                          // bound = f * 2^e, f in [0.5, 1)
+            e = 14 - e;                                       // bound * 2^e in [2^13, 2^14): fp16-safe
+        }
+        e = max(-100, min(100, e));
+        reinterpret_cast<float *>(prm)[0] = ldexpf(1.0f, e);
+        prm[1] = 0u;
+    }
+}
+
+// one warp per row: fp16 copy of (x - mean) * scale, zero padded to dim_pad; squared norm of the
+// unrounded values; rows >= n are zero with norm = pad_norm
+__global__ void __launch_bounds__(256)
+tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim, int dim_pad,
+                  const float *__restrict__ mean, const uint32_t *__restrict__ prm, __half *__restrict__ x16,
+                  float *__restrict__ norm2, float pad_norm, uint32_t *__restrict__ max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_pad) return;
+    const float scale = __uint_as_float(prm[0]);
+    __half *dst = x16 + row * dim_pad;
+    float acc = 0.f;
+    if (row < n) {
+        const float *src = x + row * dim;
+        for (int c = lane * 2; c < dim_pad; c += 64) {
+            float v0 = (c < dim) ? (src[c] - mean[c]) * scale : 0.f;
+            float v1 = (c + 1 < dim) ? (src[c + 1] - mean[c + 1]) * scale : 0.f;
+            acc = fmaf(v0, v0, acc);
+            acc = fmaf(v1, v1, acc);
+            *reinterpret_cast<__half2 *>(dst + c) = __floats2half2_rn(v0, v1);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            norm2[row] = acc;
+            if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(acc));
+        }
+    } else {
+        for (int c = lane * 2; c < dim_pad; c += 64) *reinterpret_cast<__half2 *>(dst + c) = __floats2half2_rn(0.f, 0.f);
+        if (lane == 0) norm2[row] = pad_norm;
+    }
+}
+
+// ------------------------------------------------------------------ candidates (tcgen05)
+// replace the heap root (largest kept score) by (s, j) and restore the heap; returns the new root
+__device__ __noinline__ float heap_replace_root(float *__restrict__ sc, int32_t *__restrict__ id, float s, int32_t j) {
+    int i = 0;
+    while (true) {
+        int l = 2 * i + 1;
+        if (l >= TC_KP) break;
+        int r = l + 1;
+        float sl = sc[l * TC_BM];
+        float sr = (r < TC_KP) ? sc[r * TC_BM] : -F_INF;
+        int c = (sr > sl) ? r : l;
+        float sv = fmaxf(sl, sr);
+        if (!(sv > s)) break;
+        sc[i * TC_BM] = sv;
+        id[i * TC_BM] = id[c * TC_BM];
+        i = c;
+    }
+    sc[i * TC_BM] = s;
+    id[i * TC_BM] = j;
+    return sc[0];
+}
+
+struct TcParams {
+    const float *ynorm;      // [n_db_pad]  |Y_j|^2 (+inf on padding rows)
+    int n_kblocks;           // dim_pad / 64
+    int n_tiles;             // n_db_pad / 256
+    int tiles_per_split;
+    int n_splits;
+    int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
+    float *cand_score;       // same layout
+    float *tau;              // [n_qblocks][n_splits][128]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
+                         const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stage_base = smem;
+    float *list_sc = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    int32_t *list_id = reinterpret_cast<int32_t *>(list_sc + TC_KP * TC_BM);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES);
+    uint64_t *full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
+    uint64_t *empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
+    uint64_t *acc_full = bars + 2 * TC_STAGES;       // [2]          MMA -> epilogue
+    uint64_t *acc_empty = bars + 2 * TC_STAGES + 2;  // [2]          epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qblock = blockIdx.x, split = blockIdx.y;
+    const int t0 = split * p.tiles_per_split;
+    const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+    const int n_my_tiles = max(0, t1 - t0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_db)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(2 * TC_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *a_dst = stage_base + stage * TC_STAGE_BYTES;
+                    uint8_t *b_dst = a_dst + TC_A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                    tma_load_2d(a_dst, &tm_q, &full_bar[stage], kb * TC_BK, qblock * TC_BM);
+                    tma_load_2d(b_dst, &tm_db, &full_bar[stage], kb * TC_BK, t * TC_BN);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_my_tiles; ++it) {
+                const int acc = it & 1;
+                mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                for (int kb = 0; kb < p.n_kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+                    const uint64_t adesc = umma_smem_desc(a_addr);
+                    const uint64_t bdesc = umma_smem_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (2 x 16 B) per UMMA_K = 16 halfs
+                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
+                    if (kb == p.n_kblocks - 1) umma_commit(&acc_full[acc]);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: fused per-row top-K' =====
+        const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31
+        const int row = quarter * 32 + lane;
+        float *sc = list_sc + row;
+        int32_t *id = list_id + row;
+        for (int s = 0; s < TC_KP; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
+        float tau = F_INF;
+        for (int it = 0; it < n_my_tiles; ++it) {
+            const int acc = it & 1;
+            const int n0 = (t0 + it) * TC_BN;
+            mbar_wait(&acc_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c * 32, v);
+                float4 yn[8];
+                const float4 *yp = reinterpret_cast<const float4 *>(p.ynorm + n0 + c * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) yn[i] = __ldg(yp + i);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float y = (i & 3) == 0 ? yn[i >> 2].x : (i & 3) == 1 ? yn[i >> 2].y : (i & 3) == 2 ? yn[i >> 2].z : yn[i >> 2].w;
+                    const float s = fmaf(-2.0f, __uint_as_float(v[i]), y);
+                    const bool hit = s < tau;
+                    if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) tau = heap_replace_root(sc, id, s, n0 + c * 32 + i);
+                        __syncwarp();
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        // flush: [qblock][split][slot][row] keeps the stores coalesced
+        const int64_t base = ((int64_t)qblock * p.n_splits + split) * TC_KP * TC_BM;
+        for (int s = 0; s < TC_KP; ++s) {
+            p.cand_idx[base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
+            p.cand_score[base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
+        }
+        p.tau[((int64_t)qblock * p.n_splits + split) * TC_BM + row] = tau;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ certify + canonical fp32 rescoring
+struct RsParams {
+    const float *query;      // fp32 originals
+    const float *db;
+    int64_t n_query, n_db;
+    int dim, k, exclude_self;
+    int64_t query_index_base;
+    const float *xnorm;      // [n_query_pad] |X_q|^2 (centred, scaled)
+    const uint32_t *prm;     // prm[1] = largest |Y|^2 bits
+    int n_splits;
+    const int32_t *cand_idx;
+    const float *cand_score;
+    const float *tau;
+    float c_rel;             // error bound of -2 X.Y relative to |X||Y|
+    float c_norm;            // relative error bound of the fp32 norm |Y|^2
+    float gamma;             // relative error bound of the canonical fp32 squared distance
+    int32_t *out_idx;
+    float *out_dist;
+    int32_t *stats;          // [0] rows needing the exhaustive kernel, [1] candidates rescored, [2] rows certified
+    int32_t *fallback_rows;
+};
+
+constexpr int RS_WARPS = 8;
+constexpr int RS_TS = 33;    // tile row stride (floats): conflict-free transposed access
+
+template <bool VEC4>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+knn_tc_rescore_kernel(const RsParams p) {
+    __shared__ float s_tile[RS_WARPS][32 * RS_TS];
+    __shared__ int32_t s_p[RS_WARPS][RS_PMAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (q >= p.n_query) return;
+    const int qblock = (int)(q / TC_BM), r = (int)(q % TC_BM);
+    const int n_cand = p.n_splits * TC_KP;                     // <= 512
+    const int64_t qglob = q + p.query_index_base;
+    const int64_t base = (int64_t)qblock * p.n_splits * TC_KP * TC_BM;
+
+    // gather this row's candidates: entry e = split * KP + slot
+    constexpr int PER_LANE = 16;
+    float cs[PER_LANE];
+    int32_t ci[PER_LANE];
+    float tau = F_INF;
+#pragma unroll
+    for (int u = 0; u < PER_LANE; ++u) {
+        int e = u * 32 + lane;
+        cs[u] = F_INF;
+        ci[u] = -1;
+        if (e < n_cand) {
+            int32_t j = p.cand_idx[base + (int64_t)e * TC_BM + r];
+            float s = p.cand_score[base + (int64_t)e * TC_BM + r];
+            bool self = p.exclude_self && (int64_t)j == qglob;
+            if (j >= 0 && j < p.n_db && !self) { cs[u] = s; ci[u] = j; }
+        }
+    }
+    for (int s = lane; s < p.n_splits; s += 32) tau = fminf(tau, p.tau[((int64_t)qblock * p.n_splits + s) * TC_BM + r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+
+    // k-th smallest approximate score (k rounds of extract-min over (score, entry) keys)
+    float kth = -F_INF;
+    {
+        uint64_t last = 0ull;
+        bool first = true;
+        for (int round = 0; round < p.k; ++round) {
+            uint64_t best = ~0ull;
+#pragma unroll
+            for (int u = 0; u < PER_LANE; ++u) {
+                if (ci[u] < 0) continue;
+                // order-preserving key: scores may be negative
+                uint32_t b = __float_as_uint(cs[u]);
+                b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                uint64_t key = ((uint64_t)b << 32) | (uint32_t)(u * 32 + lane);
+                if ((first || key > last) && key < best) best = key;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other < best ? other : best;
+            }
+            if (best == ~0ull) { kth = F_INF; break; }             // fewer than k candidates
+            last = best;
+            first = false;
+            uint32_t b = (uint32_t)(best >> 32);
+            b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+            kth = __uint_as_float(b);
+        }
+    }
+    const float x2 = p.xnorm[q];
+    const float ymax2 = __uint_as_float(p.prm[1]);
+    // |S~ - S| <= eps for every db point; the few ulps of the epilogue's own fp32 ops are in c_rel
+    const float eps = p.c_rel * sqrtf(x2) * sqrtf(ymax2) + p.c_norm * ymax2;
+    const float upper = kth + eps;                              // >= true k-th smallest score
+    const float margin = 2.2f * p.gamma * fmaxf(upper + x2, 0.f) + 1e-30f;
+    const float cut = upper + margin;                           // true score above this: cannot be in the top k
+    bool certified = (kth < F_INF) && (tau - eps > cut);
+    // candidates that can still be in the top k
+    int np = 0;
+    if (certified) {
+#pragma unroll
+        for (int u = 0; u < PER_LANE; ++u) {
+            bool keep = ci[u] >= 0 && (cs[u] - eps <= cut);
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            int pos = np + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < RS_PMAX) s_p[warp][pos] = ci[u];
+            np += __popc(m);
+        }
+        if (np > RS_PMAX || np < p.k) certified = false;
+    }
+    if (!certified) {
+        if (lane == 0) {
+            int slot = atomicAdd(&p.stats[0], 1);
+            p.fallback_rows[slot] = (int32_t)q;
+        }
+        return;
+    }
+    __syncwarp();
+    if (lane == 0) { atomicAdd(&p.stats[1], np); atomicAdd(&p.stats[2], 1); }
+
+    // canonical fp32 distances (oracle/knn_oracle.c): acc = fmaf(x[t]-y[t], x[t]-y[t], acc), t ascending
+    const float *xq = p.query + q * (int64_t)p.dim;
+    float *tile = s_tile[warp];
+    uint64_t keys[RS_PMAX / 32];
+#pragma unroll
+    for (int g = 0; g < RS_PMAX / 32; ++g) {
+        keys[g] = ~0ull;
+        if (g * 32 >= np) continue;                             // warp-uniform
+        const int my = g * 32 + lane;
+        const int32_t my_j = my < np ? s_p[warp][my] : -1;
+        float acc = 0.f;
+        for (int tb = 0; tb < p.dim; tb += 32) {
+            const float xv = (tb + lane < p.dim) ? xq[tb + lane] : 0.f;
+            __syncwarp();
+            if (VEC4) {
+                // 8 lanes fetch one candidate's 32 floats (128 B); 4 candidates per instruction
+                const int part = lane & 7;
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int c = rr * 4 + (lane >> 3);
+                    const int cj = g * 32 + c < np ? s_p[warp][g * 32 + c] : -1;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cj >= 0 && tb + part * 4 < p.dim)
+                        v = __ldg(reinterpret_cast<const float4 *>(p.db + (int64_t)cj * p.dim + tb + part * 4));
+                    tile[(part * 4 + 0) * RS_TS + c] = v.x;
+                    tile[(part * 4 + 1) * RS_TS + c] = v.y;
+                    tile[(part * 4 + 2) * RS_TS + c] = v.z;
+                    tile[(part * 4 + 3) * RS_TS + c] = v.w;
+                }
+            } else {
+                for (int c = 0; c < 32; ++c) {
+                    const int cj = g * 32 + c < np ? s_p[warp][g * 32 + c] : -1;
+                    float v = 0.f;
+                    if (cj >= 0 && tb + lane < p.dim) v = __ldg(p.db + (int64_t)cj * p.dim + tb + lane);
+                    tile[lane * RS_TS + c] = v;
+                }
+            }
+            __syncwarp();
+            const int tn = min(32, p.dim - tb);
+            for (int t = 0; t < tn; ++t) {
+                const float x = __shfl_sync(0xffffffffu, xv, t);
+                const float diff = x - tile[t * RS_TS + lane];
+                acc = fmaf(diff, diff, acc);
+            }
+        }
+        if (my_j >= 0) keys[g] = dist_key(sqrtf(acc), my_j);
+    }
+    // rank by counting; keys are distinct (distinct indices)
+#pragma unroll
+    for (int g = 0; g < RS_PMAX / 32; ++g) {
+        if (g * 32 >= np) continue;
+        int rank = 0;
+#pragma unroll
+        for (int h = 0; h < RS_PMAX / 32; ++h) {
+            if (h * 32 >= np) continue;
+            for (int l = 0; l < 32; ++l) {
+                uint64_t other = __shfl_sync(0xffffffffu, keys[h], l);
+                rank += other < keys[g] ? 1 : 0;
+            }
+        }
+        if (keys[g] != ~0ull && rank < p.k) {
+            p.out_idx[q * p.k + rank] = key_idx(keys[g]);
+            p.out_dist[q * p.k + rank] = key_dist(keys[g]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const __half *base, int64_t rows, int dim_pad, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return MMU_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)dim_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dim_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)rc); return MMU_ERR_CUDA; }
+    return MMU_OK;
+}
+
+static inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct TcLayout {
+    int64_t q_pad, n_pad;
+    int dim_pad, n_qblocks, n_tiles, n_splits, tiles_per_split, stat_blocks, rows_per_stat_block;
+    bool shared_operand;
+    size_t off_prm, off_mean, off_partial, off_db16, off_ynorm, off_q16, off_xnorm, off_cidx, off_cscore, off_tau, total;
+};
+
+static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_operand) {
+    TcLayout L;
+    L.shared_operand = shared_operand;
+    L.dim_pad = (int)round_up(dim, TC_BK);
+    L.n_pad = round_up(n_db, TC_BN);                 // also a multiple of TC_BM
+    L.q_pad = shared_operand ? L.n_pad : round_up(n_query, TC_BM);
+    L.n_qblocks = (int)(round_up(n_query, TC_BM) / TC_BM);
+    L.n_tiles = (int)(L.n_pad / TC_BN);
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    // split the db range so that the grid fills whole waves (one CTA per SM)
+    int best_s = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 8 && s <= L.n_tiles; ++s) {
+        if (s > 1 && L.n_tiles / s < 4) break;
+        double waves = (double)L.n_qblocks * s / sms;
+        double eff = waves / (double)((int64_t)waves + (waves > (int64_t)waves ? 1 : 0));
+        if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
+    }
+    L.n_splits = best_s;
+    L.tiles_per_split = (L.n_tiles + L.n_splits - 1) / L.n_splits;
+    L.stat_blocks = (int)((n_db + 511) / 512 < 296 ? (n_db + 511) / 512 : 296);
+    if (L.stat_blocks < 1) L.stat_blocks = 1;
+    L.rows_per_stat_block = (int)((n_db + L.stat_blocks - 1) / L.stat_blocks);
+    size_t o = 0;
+    L.off_prm = o; o += 256;
+    L.off_mean = o; o += align256(sizeof(float) * L.dim_pad);
+    L.off_partial = o; o += align256(sizeof(float) * (size_t)296 * dim) * (shared_operand ? 1 : 2);
+    L.off_db16 = o; o += align256(sizeof(__half) * (size_t)L.n_pad * L.dim_pad);
+    L.off_ynorm = o; o += align256(sizeof(float) * (size_t)L.n_pad);
+    L.off_q16 = o; if (!shared_operand) o += align256(sizeof(__half) * (size_t)L.q_pad * L.dim_pad);
+    L.off_xnorm = o; o += align256(sizeof(float) * (size_t)L.q_pad);
+    size_t cand = (size_t)L.n_qblocks * L.n_splits * TC_KP * TC_BM;
+    L.off_cidx = o; o += align256(sizeof(int32_t) * cand);
+    L.off_cscore = o; o += align256(sizeof(float) * cand);
+    L.off_tau = o; o += align256(sizeof(float) * (size_t)L.n_qblocks * L.n_splits * TC_BM);
+    L.total = o;
+    return L;
+}
+
+}  // namespace mmu
+
+extern "C" size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db) {
+    if (n_query <= 0 || n_db <= 0 || dim <= 0) return 0;
+    return mmu::tc_layout(n_query, n_db, dim, query_is_db != 0).total;
+}
+
+extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
+                          int exclude_self, int64_t query_index_base, int query_is_db, void *workspace,
+                          size_t workspace_bytes, int32_t *out_idx, float *out_dist, int32_t *stats,
+                          int32_t *fallback_rows, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(query && db && workspace && out_idx && out_dist && stats && fallback_rows, "mmu_knn_tc: null pointer");
+    MMU_CHECK_ARG(k >= 1 && k <= MMU_KNN_TC_MAX_K, "mmu_knn_tc: k=%d outside [1,%d]", k, MMU_KNN_TC_MAX_K);
+    MMU_CHECK_ARG(dim >= 1 && n_db >= 1 && n_query >= 0, "mmu_knn_tc: bad sizes");
+    MMU_CHECK_ARG(n_db < (int64_t)2147483647 - TC_BN, "mmu_knn_tc: db index exceeds int32");
+    MMU_CHECK_ARG(!query_is_db || (query == db && n_query == n_db && query_index_base == 0),
+                  "mmu_knn_tc: query_is_db requires identical query and db");
+    cudaStream_t st = as_stream(stream);
+    MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
+    if (n_query == 0) return MMU_OK;
+    const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0);
+    MMU_CHECK_ARG(workspace_bytes >= L.total, "mmu_knn_tc: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mmu_knn_tc: workspace must be 256-byte aligned");
+    uint8_t *ws = static_cast<uint8_t *>(workspace);
+    uint32_t *prm = reinterpret_cast<uint32_t *>(ws + L.off_prm);
+    float *mean = reinterpret_cast<float *>(ws + L.off_mean);
+    float *partial = reinterpret_cast<float *>(ws + L.off_partial);
+    __half *db16 = reinterpret_cast<__half *>(ws + L.off_db16);
+    float *ynorm = reinterpret_cast<float *>(ws + L.off_ynorm);
+    __half *q16 = L.shared_operand ? db16 : reinterpret_cast<__half *>(ws + L.off_q16);
+    float *xnorm = L.shared_operand ? ynorm : reinterpret_cast<float *>(ws + L.off_xnorm);
+    int32_t *cidx = reinterpret_cast<int32_t *>(ws + L.off_cidx);
+    float *cscore = reinterpret_cast<float *>(ws + L.off_cscore);
+    float *tau = reinterpret_cast<float *>(ws + L.off_tau);
+
+    // ---- prep
+    MMU_CUDA(cudaMemsetAsync(prm, 0, 256, st));
+    tc_colsum_kernel<<<L.stat_blocks, 256, 0, st>>>(db, n_db, dim, L.rows_per_stat_block, partial, prm + 2);
+    int launches = 1;
+    if (!L.shared_operand) {
+        // the queries only contribute to the range of the common scale
+        int qb = (int)((n_query + 511) / 512 < 296 ? (n_query + 511) / 512 : 296);
+        int rpb = (int)((n_query + qb - 1) / qb);
+        // the queries' partial sums are not used: they go to the second half of the scratch area
+        float *scratch = partial + (size_t)296 * dim;
+        tc_colsum_kernel<<<qb, 256, 0, st>>>(query, n_query, dim, rpb, scratch, prm + 2);
+        ++launches;
+    }
+    tc_finish_stats_kernel<<<1, 1024, 0, st>>>(partial, L.stat_blocks, dim, n_db, mean, prm, 1);
+    tc_convert_kernel<<<(unsigned)((L.n_pad * 32 + 255) / 256), 256, 0, st>>>(db, n_db, L.n_pad, dim, L.dim_pad, mean, prm,
+                                                                              db16, ynorm, HUGE_VALF, prm + 1);
+    launches += 2;
+    if (!L.shared_operand) {
+        tc_convert_kernel<<<(unsigned)((L.q_pad * 32 + 255) / 256), 256, 0, st>>>(query, n_query, L.q_pad, dim, L.dim_pad,
+                                                                                  mean, prm, q16, xnorm, 0.f, nullptr);
+        ++launches;
+    }
+    MMU_LAUNCH_CHECK_N(launches);
+
+    // ---- candidates
+    CUtensorMap tm_q, tm_db;
+    int rc = make_map(&tm_q, q16, L.q_pad, L.dim_pad, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tm_db, db16, L.n_pad, L.dim_pad, TC_BN);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    TcParams tp;
+    tp.ynorm = ynorm;
+    tp.n_kblocks = L.dim_pad / TC_BK;
+    tp.n_tiles = L.n_tiles;
+    tp.tiles_per_split = L.tiles_per_split;
+    tp.n_splits = L.n_splits;
+    tp.cand_idx = cidx;
+    tp.cand_score = cscore;
+    tp.tau = tau;
+    knn_tc_candidates_kernel<<<dim3(L.n_qblocks, L.n_splits), TC_THREADS, TC_SMEM_BYTES, st>>>(tm_q, tm_db, tp);
+    MMU_LAUNCH_CHECK();
+
+    // ---- certify + rescore
+    RsParams rp;
+    rp.query = query; rp.db = db; rp.n_query = n_query; rp.n_db = n_db; rp.dim = dim; rp.k = k;
+    rp.exclude_self = exclude_self; rp.query_index_base = query_index_base;
+    rp.xnorm = xnorm; rp.prm = prm; rp.n_splits = L.n_splits;
+    rp.cand_idx = cidx; rp.cand_score = cscore; rp.tau = tau;
+    // fp16 rounding of both operands (2 * 2^-11 on each product, x2 for the -2 factor, 1% headroom) plus
+    // the fp32 accumulation across dim_pad/16 MMAs and the final fma
+    rp.c_rel = 1.01f * 0x1p-9f + ((float)(L.dim_pad / 16) + 16.f) * 0x1p-22f;
+    rp.c_norm = ((float)(L.dim_pad / 32) + 8.f) * 0x1p-23f;      // lane-strided fma chain + warp tree + final fma
+    rp.gamma = ((float)dim + 4.f) * 0x1p-24f;
+    rp.out_idx = out_idx; rp.out_dist = out_dist; rp.stats = stats; rp.fallback_rows = fallback_rows;
+    unsigned rblocks = (unsigned)((n_query + RS_WARPS - 1) / RS_WARPS);
+    bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0);
+    if (vec4) knn_tc_rescore_kernel<true><<<rblocks, RS_WARPS * 32, 0, st>>>(rp);
+    else knn_tc_rescore_kernel<false><<<rblocks, RS_WARPS * 32, 0, st>>>(rp);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}

@@ -95,7 +95,7 @@ def knn_exact_simt(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: 
 
 def available_knn_methods():
     """kNN engines compiled into the library ("tc" needs the mmu_knn_tc_* entry points)."""
-    return ("simt", "tc") if hasattr(lib(), "mmu_knn_tc_candidates") else ("simt",)
+    return ("simt", "tc") if hasattr(lib(), "mmu_knn_tc") else ("simt",)
 
 
 def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, method: str | None = None):
@@ -112,6 +112,9 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         with profiler.stage("knn", flops=flops, kernel="knn_exact_f32_kernel"):
             return knn_exact_simt(query, db, k, exclude_self)
     if method == "tc":
+        if k > native.KNN_TC_MAX_K:            # the per-row candidate lists hold 64 entries
+            with profiler.stage("knn", flops=flops, kernel="knn_exact_f32_kernel"):
+                return knn_exact_simt(query, db, k, exclude_self)
         from .knn_tc import knn_tc
         with profiler.stage("knn", flops=flops, kernel="knn_tc"):
             return knn_tc(query, db, k, exclude_self)

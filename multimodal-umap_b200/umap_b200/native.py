@@ -15,6 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libmmumap_b200.so")
 
 MAX_K = 64
+KNN_TC_MAX_K = 32
 OPT_STATE_WORDS = 8
 SIGMA_BISECT = 0
 SIGMA_NEWTON = 1
@@ -32,6 +33,9 @@ _SIGNATURES = {
     "mmu_device_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_exact_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
                                   c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "mmu_knn_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p, c_size_t,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_smooth_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),

@@ -1,0 +1,110 @@
+"""GPU parity tests of the tensor-core kNN path (mmu_knn_tc: tcgen05 candidates + certification +
+canonical fp32 rescoring, exhaustive fallback for uncertified rows) against the CPU oracle
+(oracle/knn_oracle.c, the exhaustive restatement of /root/reference/impl/model.py:109,163,181-193)
+and, at sizes the oracle cannot finish in seconds, against the exhaustive CUDA-core kernel.
+Bar: indices AND fp32 distance bit patterns identical."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import umap_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _blobs(n, d, centers, seed, spread=5.0, noise=1.0):
+    rng = np.random.default_rng(seed)
+    c = rng.standard_normal((centers, d)) * spread
+    return (c[rng.integers(0, centers, n)] + noise * rng.standard_normal((n, d))).astype(np.float32)
+
+
+def _tc(q, db, k, excl):
+    from umap_b200 import knn_tc
+    i, d = knn_tc.knn_tc(q, db, k, excl)
+    torch.cuda.synchronize()
+    return i.cpu().numpy(), d.cpu().numpy(), dict(knn_tc.last_stats)
+
+
+def _same(a_idx, a_dist, b_idx, b_dist):
+    assert np.array_equal(a_idx, b_idx), f"{(a_idx != b_idx).any(axis=1).sum()} rows differ"
+    assert np.array_equal(a_dist.view(np.uint32), b_dist.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,d,k", [(700, 37, 15), (3000, 64, 15), (1500, 200, 30), (513, 768, 5), (130, 5, 7)])
+def test_fit_mode_bit_exact_vs_oracle(n, d, k):
+    x = _blobs(n, d, 6, n + d)
+    xt = torch.from_numpy(x).cuda()
+    ti, td, st = _tc(xt, xt, k, True)
+    oi, od = orc.knn_exact(x, x, k, True)
+    _same(ti, td, oi, od)
+    assert st["rows"] == n
+
+
+def test_query_mode_bit_exact_vs_oracle():
+    db = _blobs(2100, 96, 5, 1)
+    q = _blobs(333, 96, 5, 2)
+    ti, td, _ = _tc(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), 15, False)
+    oi, od = orc.knn_exact(q, db, 15, False)
+    _same(ti, td, oi, od)
+
+
+def test_uncentred_large_offset_data():
+    """A large common offset (BERT-pooler-like bias) must not cost exactness: the prep centres it."""
+    x = _blobs(2000, 128, 8, 3, spread=1.0) + np.float32(40.0)
+    xt = torch.from_numpy(x).cuda()
+    ti, td, st = _tc(xt, xt, 15, True)
+    oi, od = orc.knn_exact(x, x, 15, True)
+    _same(ti, td, oi, od)
+    assert st["fallback_rows"] < 0.05 * st["rows"], st
+
+
+def test_duplicates_and_exact_ties_fall_back_correctly():
+    """Many exact duplicates: distance ties broken by index; rows the bound cannot certify must
+    be finished by the exhaustive kernel and still match the oracle bit for bit."""
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((40, 24)).astype(np.float32)
+    x = base[rng.integers(0, 40, 1200)]                     # every row has ~30 exact copies
+    xt = torch.from_numpy(x).cuda()
+    ti, td, st = _tc(xt, xt, 15, True)
+    oi, od = orc.knn_exact(x, x, 15, True)
+    _same(ti, td, oi, od)
+    # >64 identical copies of each row exceed the candidate list: certification must fail there
+    y = base[rng.integers(0, 8, 1500)]
+    yt = torch.from_numpy(y).cuda()
+    ti, td, st = _tc(yt, yt, 15, True)
+    oi, od = orc.knn_exact(y, y, 15, True)
+    _same(ti, td, oi, od)
+    assert st["fallback_rows"] > 0
+
+
+def test_constant_and_tiny_inputs():
+    x = np.zeros((300, 16), np.float32)
+    xt = torch.from_numpy(x).cuda()
+    ti, td, _ = _tc(xt, xt, 5, True)
+    oi, od = orc.knn_exact(x, x, 5, True)
+    _same(ti, td, oi, od)
+    x = _blobs(40, 8, 2, 9)
+    xt = torch.from_numpy(x).cuda()
+    ti, td, _ = _tc(xt, xt, 10, True)
+    oi, od = orc.knn_exact(x, x, 10, True)
+    _same(ti, td, oi, od)
+
+
+@pytest.mark.parametrize("n,d,kind", [(20000, 256, "blobs"), (12000, 768, "bert"), (6000, 4096, "vae")])
+def test_matches_exhaustive_cuda_kernel_at_scale(n, d, kind):
+    """Shapes of BASELINE.json configs[1] (BERT 768-D, SD-VAE 4096-D): the tensor-core path must
+    equal the exhaustive fp32 kernel everywhere and certify nearly every row itself."""
+    from umap_b200 import graph as G
+    g = torch.Generator(device="cuda").manual_seed(n)
+    cl = torch.arange(n, device="cuda") % 64
+    if kind == "bert":
+        x = torch.tanh(torch.randn((64, d), generator=g, device="cuda")[cl] + 0.5 * torch.randn((n, d), generator=g, device="cuda"))
+    elif kind == "vae":
+        x = 2.0 * torch.randn((64, d), generator=g, device="cuda")[cl] + 4.0 * torch.randn((n, d), generator=g, device="cuda")
+    else:
+        x = 5.0 * torch.randn((64, d), generator=g, device="cuda")[cl] + torch.randn((n, d), generator=g, device="cuda")
+    x = x.contiguous()
+    ti, td, st = _tc(x, x, 15, True)
+    si, sd = G.knn_exact_simt(x, x, 15, True)
+    _same(ti, td, si.cpu().numpy(), sd.cpu().numpy())
+    assert st["fallback_rows"] <= 0.02 * n, st
