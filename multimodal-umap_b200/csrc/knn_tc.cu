@@ -38,8 +38,10 @@ constexpr int TC_KP = 64;         // candidates kept per row and db split
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8;
+constexpr int TC_CH = 16;         // accumulator columns scanned per epilogue step
+constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4 + TC_CH * TC_BM * 4;   // slots + group maxima + scan buffer
 constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES + 256;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int RS_PMAX = 128;      // most candidates rescored per row
 #define F_INF __int_as_float(0x7f800000)
 
@@ -97,6 +99,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
 }
@@ -196,25 +207,37 @@ tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim
 }
 
 // ------------------------------------------------------------------ candidates (tcgen05)
-// replace the heap root (largest kept score) by (s, j) and restore the heap; returns the new root
-__device__ __noinline__ float heap_replace_root(float *__restrict__ sc, int32_t *__restrict__ id, float s, int32_t j) {
-    int i = 0;
-    while (true) {
-        int l = 2 * i + 1;
-        if (l >= TC_KP) break;
-        int r = l + 1;
-        float sl = sc[l * TC_BM];
-        float sr = (r < TC_KP) ? sc[r * TC_BM] : -F_INF;
-        int c = (sr > sl) ? r : l;
-        float sv = fmaxf(sl, sr);
-        if (!(sv > s)) break;
-        sc[i * TC_BM] = sv;
-        id[i * TC_BM] = id[c * TC_BM];
-        i = c;
+// Per-row candidate list: TC_KP slots in 8-slot groups, slot-major in shared memory (address =
+// slot * 128 + row, so the 32 rows of a warp always hit 32 different banks), with the maximum of
+// every group cached in `gmax`.  The owner thread keeps the list maximum `tau` and its group
+// `gstar` in registers.  Replacing the maximum costs two rounds of independent loads (the 8 slots
+// of one group, then the 8 group maxima) instead of a pointer-chasing heap walk.
+constexpr int TC_GROUPS = TC_KP / 8;
+__device__ __forceinline__ void list_replace_max(float *__restrict__ sc, int32_t *__restrict__ id,
+                                                 float *__restrict__ gmax, float s, int32_t j, float &tau, int &gstar) {
+    float e[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) e[u] = sc[(gstar * 8 + u) * TC_BM];
+    int pos = 0;
+    float m = e[0];
+#pragma unroll
+    for (int u = 1; u < 8; ++u)
+        if (e[u] > m) { m = e[u]; pos = u; }
+    float ng = s;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ng = fmaxf(ng, (u == pos) ? s : e[u]);
+    sc[(gstar * 8 + pos) * TC_BM] = s;
+    id[(gstar * 8 + pos) * TC_BM] = j;
+    gmax[gstar * TC_BM] = ng;
+    float best = ng;
+    int bg = gstar;
+#pragma unroll
+    for (int g = 0; g < TC_GROUPS; ++g) {
+        float gm = gmax[g * TC_BM];
+        if (g != gstar && gm > best) { best = gm; bg = g; }
     }
-    sc[i * TC_BM] = s;
-    id[i * TC_BM] = j;
-    return sc[0];
+    tau = best;
+    gstar = bg;
 }
 
 struct TcParams {
@@ -231,11 +254,14 @@ struct TcParams {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                          const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (128-byte swizzle atoms) comes from the declaration, so that every pointer
+    // below keeps its shared-memory provenance and compiles to LDS/STS
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *stage_base = smem;
     float *list_sc = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
     int32_t *list_id = reinterpret_cast<int32_t *>(list_sc + TC_KP * TC_BM);
+    float *list_gmax = reinterpret_cast<float *>(list_id + TC_KP * TC_BM);
+    float *scan_buf = list_gmax + TC_GROUPS * TC_BM;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES);
     uint64_t *full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
     uint64_t *empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
@@ -245,6 +271,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qblock = blockIdx.x, split = blockIdx.y;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
     const int n_my_tiles = max(0, t1 - t0);
@@ -316,8 +343,12 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         const int row = quarter * 32 + lane;
         float *sc = list_sc + row;
         int32_t *id = list_id + row;
+        float *gmax = list_gmax + row;
+        float *sq = scan_buf + row;
         for (int s = 0; s < TC_KP; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
+        for (int g = 0; g < TC_GROUPS; ++g) gmax[g * TC_BM] = F_INF;
         float tau = F_INF;
+        int gstar = 0;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int acc = it & 1;
             const int n0 = (t0 + it) * TC_BN;
@@ -325,22 +356,30 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN;
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);
-                float4 yn[8];
-                const float4 *yp = reinterpret_cast<const float4 *>(p.ynorm + n0 + c * 32);
+            for (int c = 0; c < TC_BN / TC_CH; ++c) {
+                uint32_t v[TC_CH];
+                tmem_ld_32x16(taddr + c * TC_CH, v);
+                float4 yn[TC_CH / 4];
+                const float4 *yp = reinterpret_cast<const float4 *>(p.ynorm + n0 + c * TC_CH);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) yn[i] = __ldg(yp + i);
+                for (int i = 0; i < TC_CH / 4; ++i) yn[i] = __ldg(yp + i);
                 tmem_ld_wait();
+                // branch-free scan: scores to the scan buffer, hits to a bit mask
+                uint32_t mask = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < TC_CH; ++i) {
                     const float y = (i & 3) == 0 ? yn[i >> 2].x : (i & 3) == 1 ? yn[i >> 2].y : (i & 3) == 2 ? yn[i >> 2].z : yn[i >> 2].w;
                     const float s = fmaf(-2.0f, __uint_as_float(v[i]), y);
-                    const bool hit = s < tau;
-                    if (__any_sync(0xffffffffu, hit)) {
-                        if (hit) tau = heap_replace_root(sc, id, s, n0 + c * 32 + i);
-                        __syncwarp();
+                    sq[i * TC_BM] = s;
+                    mask |= (s < tau) ? (1u << i) : 0u;
+                }
+                // drain: each lane inserts its own hits (rare after the first tiles)
+                while (__any_sync(0xffffffffu, mask != 0u)) {
+                    if (mask) {
+                        const int i = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float s = sq[i * TC_BM];
+                        if (s < tau) list_replace_max(sc, id, gmax, s, n0 + c * TC_CH + i, tau, gstar);
                     }
                 }
             }
