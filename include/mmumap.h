@@ -168,13 +168,16 @@ int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_s
  * neg: [n_kept x num_rep] host-generated negative ids (ref: model.py:444) or NULL to draw
  * them on the device (Philox, uniform in [0, rep_count)).
  * kept_count: device scalar (number of valid entries of kept_pos).
- * loss (nullable): device float accumulating the modality's loss. */
+ * loss (nullable): device float accumulating the modality's loss.
+ * fast_math != 0: s^b through ex2/lg2 and an approximate reciprocal (relative error of a force
+ * coefficient <= ~1e-5; meant for the device sample stream); 0 = powf and IEEE division, the
+ * arithmetic the parity tests pin to the reference. */
 int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
                     const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
                     int n_batches, int batch_size, int num_rep, int64_t rep_count,
                     const float *head, const float *tail, float *grad_head, float *grad_tail,
                     int dim, float a, float b, uint64_t seed, const uint32_t *state, float *loss,
-                    mmu_stream_t stream);
+                    int fast_math, mmu_stream_t stream);
 
 /* K8: InfoNCE gradient for one direction (anchors e0 -> positives/negatives e1).
  * ref: model.py:364-394.  perm [num] (nullable = identity) and neg [num x n_neg] (nullable =

@@ -224,6 +224,145 @@ edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------ K7b, register-blocked variant
+// Same arithmetic as edge_forces_kernel, reorganised for instruction throughput (ncu: the loop
+// version is XU/issue bound, not memory bound): all R+1 tail rows of an edge are gathered first
+// (R+1 independent 16-byte loads in flight per lane), the R+1 scalar force coefficients are split
+// over the LANES lanes of the group instead of being recomputed by each of them, and the
+// negatives' Philox call is split the same way.  FAST selects s^b = ex2(b*lg2(s)) and an
+// approximate reciprocal (device sample stream); !FAST keeps powf/div exactly as the loop version
+// (host-replayed stream, parity tests).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool FAST>
+__device__ __forceinline__ float pair_coef(float s_raw, bool attractive, float a, float b, float sc_a, float sc_r,
+                                           bool want_loss, float &loss) {
+    if (FAST) {
+        const float s = fmaxf(s_raw, 1e-6f);
+        const float q = a * ex2_approx(b * __log2f(s));          // a s^b
+        const float opq = 1.0f + q;
+        const float num = (attractive ? sc_a : -sc_r) * 2.0f * b * q;
+        const float den = attractive ? s * opq : s * opq * fmaf(1e-6f, opq, q);
+        if (want_loss) loss = attractive ? sc_a * logf(opq) : -sc_r * logf(q / opq + 1e-6f);
+        return (s_raw >= 1e-6f) ? __fdividef(num, den) : 0.0f;
+    } else {
+        float coef, l;
+        if (attractive) { attr_terms(s_raw, a, b, coef, l); coef *= sc_a; l *= sc_a; }
+        else { rep_terms(s_raw, a, b, coef, l); coef *= sc_r; l *= sc_r; }
+        loss = l;
+        return coef;
+    }
+}
+
+template <int VEC, int LANES, int R, bool FAST>
+__global__ void __launch_bounds__(256)
+edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                      const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                      const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
+                      int batch_size, uint32_t rep_count, const float *__restrict__ head,
+                      const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
+                      float a, float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    constexpr int DIM = VEC * LANES;
+    constexpr int NP = R + 1;                                 // pairs per kept edge: 1 attractive + R repulsive
+    constexpr int NCALL = (R + 3) / 4;                        // Philox calls per edge
+    constexpr int ROUNDS = (NP + LANES - 1) / LANES;
+    const int n_kept = *kept_count;
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int gl = threadIdx.x % LANES;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+    const float inv_nb = 1.0f / (float)n_batches;
+    const bool want_loss = loss_out != nullptr;
+    float loss_acc = 0.f;
+    constexpr int64_t gpw = 32 / LANES;
+    const int64_t wfirst = (gid / gpw) * gpw;
+    for (int64_t e0 = wfirst; e0 < n_kept; e0 += n_groups) {
+        const int64_t e = e0 + (gid - wfirst);
+        const bool active = e < n_kept;
+        int32_t p = 0, i = 0;
+        uint32_t t_idx[NP];
+        float sc_a = 0.f, sc_r = 0.f;
+        t_idx[0] = 0;
+        if (active) {
+            p = kept_pos[e];
+            i = row[p];
+            t_idx[0] = (uint32_t)col[p];
+            const float kb = (float)batch_kept[i / batch_size];
+            sc_a = inv_nb / kb;
+            sc_r = inv_nb / (kb * (float)R);
+        }
+        if (neg) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) t_idx[r + 1] = active ? (uint32_t)neg[e * R + r] : 0u;
+        } else if (LANES >= NCALL) {
+            // lane c of the group evaluates call c (same counters as the loop version: identical draws)
+            const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)(gl % NCALL), epoch, STREAM_NEG, k0, k1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t mine = (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w;
+                t_idx[r + 1] = urange(__shfl_sync(0xffffffffu, mine, r >> 2, LANES), rep_count);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCALL; ++c) {
+                const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)c, epoch, STREAM_NEG, k0, k1);
+                if (4 * c + 0 < R) t_idx[4 * c + 1] = urange(w.x, rep_count);
+                if (4 * c + 1 < R) t_idx[4 * c + 2] = urange(w.y, rep_count);
+                if (4 * c + 2 < R) t_idx[4 * c + 3] = urange(w.z, rep_count);
+                if (4 * c + 3 < R) t_idx[4 * c + 4] = urange(w.w, rep_count);
+            }
+        }
+        // gather: head row + all tail rows, then differences and squared distances
+        const Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * DIM + gl * VEC);
+        Vec<VEC> df[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) df[q] = load_vec<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
+        float s[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { df[q].v[c] = yi.v[c] - df[q].v[c]; acc = fmaf(df[q].v[c], df[q].v[c], acc); }
+            s[q] = group_sum<LANES>(acc);
+        }
+        // coefficients: pair q is evaluated by lane q % LANES
+        float cv[ROUNDS];
+#pragma unroll
+        for (int t = 0; t < ROUNDS; ++t) {
+            float sv = 1.0f;
+            bool valid = false;
+#pragma unroll
+            for (int u = 0; u < LANES; ++u)
+                if (t * LANES + u < NP && gl == u) { sv = s[t * LANES + u]; valid = true; }
+            float l = 0.f;
+            const float cf = pair_coef<FAST>(sv, t == 0 && gl == 0, a, b, sc_a, sc_r, want_loss, l);
+            cv[t] = valid ? cf : 0.f;
+            if (want_loss && valid) loss_acc += l;
+        }
+        Vec<VEC> gi;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const float coef = LANES == 1 ? cv[q] : __shfl_sync(0xffffffffu, cv[q / LANES], q % LANES, LANES);
+            Vec<VEC> g;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df[q].v[c]; gi.v[c] += g.v[c]; }
+            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)t_idx[q] * DIM + gl * VEC, g, -1.0f);
+        }
+        if (active) red_vec<VEC>(grad_head + (int64_t)i * DIM + gl * VEC, gi, 1.0f);
+    }
+    if (want_loss) {
+        loss_acc = warp_sum(loss_acc);
+        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
+    }
+}
+
 // generic dimension: one warp per kept edge, lane owns components lane, lane+32, ... (dim <= 128)
 __global__ void __launch_bounds__(256)
 edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
@@ -368,6 +507,97 @@ infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64
     }
 }
 
+// K8, vectorised variant: a group of LANES lanes per anchor, each lane owning VEC consecutive
+// components (dim == VEC*LANES): the anchor row and its 1+n_neg candidate rows are gathered with
+// 16-byte loads, norms and dot products are group reductions, and the gradients leave as vector
+// red.global.add -- the same closed form as infonce_kernel (ref: model.py:364-394).
+template <int VEC, int LANES>
+__global__ void __launch_bounds__(256)
+infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num,
+                   const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
+                   float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
+                   uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    constexpr int DIM = VEC * LANES;
+    const int gl = threadIdx.x % LANES;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const bool active = t < num;
+    const int64_t tt = active ? t : 0;
+    const int64_t n_chunks = (num + chunk - 1) / chunk;
+    const int64_t cidx = tt / chunk;
+    const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
+    const float wgt = weight / ((float)clen * (float)n_chunks);           // ref: model.py:392,394
+    const int32_t i = perm ? perm[tt] : (int32_t)tt;
+    const int M = 1 + n_neg;
+    int32_t ids[NCE_MAX];
+    ids[0] = i;
+    if (neg) {
+        for (int m = 1; m < M; ++m) ids[m] = neg[tt * n_neg + (m - 1)];
+    } else {
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        Philox4 rnd = {0, 0, 0, 0};
+        for (int m = 1; m < M; ++m) {
+            int q = m - 1;
+            if ((q & 3) == 0) rnd = philox4x32_10((uint32_t)tt, (uint32_t)(q >> 2), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
+            uint32_t x = (q & 3) == 0 ? rnd.x : (q & 3) == 1 ? rnd.y : (q & 3) == 2 ? rnd.z : rnd.w;
+            ids[m] = (int32_t)urange(x, (uint32_t)num);
+        }
+    }
+    const Vec<VEC> av = load_vec<VEC>(e0 + (int64_t)i * DIM + gl * VEC);
+    float na2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) na2 = fmaf(av.v[c], av.v[c], na2);
+    const float na = fmaxf(sqrtf(group_sum<LANES>(na2)), 1e-12f);       // F.normalize eps
+    float nrm[NCE_MAX], cs[NCE_MAX];
+    float mx = -__int_as_float(0x7f800000);
+    for (int m = 0; m < M; ++m) {
+        const bool ok = m == 0 || ids[m] != i;                           // ref: model.py:386
+        const Vec<VEC> ev = load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
+        float n2 = 0.f, dt = 0.f;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) { n2 = fmaf(ev.v[c], ev.v[c], n2); dt = fmaf(av.v[c], ev.v[c], dt); }
+        n2 = group_sum<LANES>(n2);
+        dt = group_sum<LANES>(dt);
+        nrm[m] = fmaxf(sqrtf(n2), 1e-12f);
+        cs[m] = dt / (na * nrm[m]);
+        if (ok) mx = fmaxf(mx, cs[m] / temperature);
+    }
+    float den = 0.f;
+    for (int m = 0; m < M; ++m)
+        if (m == 0 || ids[m] != i) den += expf(cs[m] / temperature - mx);
+    float loss_local = (active && gl == 0) ? wgt * -(cs[0] / temperature - mx - logf(den)) : 0.f;
+    float ccs = 0.f;
+    Vec<VEC> acc;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc.v[c] = 0.f;
+    const float inv_na = 1.0f / na;
+    for (int m = 0; m < M; ++m) {
+        const bool ok = m == 0 || ids[m] != i;
+        if (!ok) continue;                                               // group-uniform
+        const float cm = expf(cs[m] / temperature - mx) / den - (m == 0 ? 1.f : 0.f);
+        ccs = fmaf(cm, cs[m], ccs);
+        const Vec<VEC> ev = load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
+        const float inv_n = 1.0f / nrm[m];
+        const float sm = wgt * cm / (temperature * nrm[m]);
+        Vec<VEC> g;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            const float vc = ev.v[c] * inv_n, uc = av.v[c] * inv_na;
+            acc.v[c] = fmaf(cm, vc, acc.v[c]);
+            g.v[c] = sm * (uc - vc * cs[m]);                             // d/d e_m = w c_m (u - v_m cos_m)/(tau |e_m|)
+        }
+        if (active) red_vec<VEC>(grad1 + (int64_t)ids[m] * DIM + gl * VEC, g, 1.0f);
+    }
+    const float sa = wgt / (temperature * na);
+    Vec<VEC> ga;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) ga.v[c] = sa * (acc.v[c] - av.v[c] * inv_na * ccs);   // d/d a
+    if (active) red_vec<VEC>(grad0 + (int64_t)i * DIM + gl * VEC, ga, 1.0f);
+    if (loss_out) {
+        loss_local = warp_sum(loss_local);
+        if ((threadIdx.x & 31) == 0 && loss_local != 0.f) atomicAdd(loss_out, loss_local);
+    }
+}
+
 // ------------------------------------------------------------------ K9: Adam
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
@@ -442,7 +672,7 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
                                const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
                                int n_batches, int batch_size, int num_rep, int64_t rep_count, const float *head,
                                const float *tail, float *grad_head, float *grad_tail, int dim, float a, float b,
-                               uint64_t seed, const uint32_t *state, float *loss, mmu_stream_t stream) {
+                               uint64_t seed, const uint32_t *state, float *loss, int fast_math, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(row && col && kept_pos && kept_count && batch_kept && head && tail && grad_head && state,
                   "mmu_edge_forces: null pointer");
@@ -456,19 +686,38 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
     edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept, n_batches, \
                                                      batch_size, num_rep, (uint32_t)rep_count, head, tail,       \
                                                      grad_head, grad_tail, dim, a, b, seed, os, loss)
+#define MMU_FORCES_RB(V, L, RR)                                                                                  \
+    do {                                                                                                         \
+        if (fast_math)                                                                                           \
+            edge_forces_rb_kernel<V, L, RR, true><<<blocks, 256, 0, st>>>(                                       \
+                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, (uint32_t)rep_count,     \
+                head, tail, grad_head, grad_tail, a, b, seed, os, loss);                                         \
+        else                                                                                                     \
+            edge_forces_rb_kernel<V, L, RR, false><<<blocks, 256, 0, st>>>(                                      \
+                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, (uint32_t)rep_count,     \
+                head, tail, grad_head, grad_tail, a, b, seed, os, loss);                                         \
+    } while (0)
+#define MMU_FORCES_DIM(V, L)                                      \
+    do {                                                          \
+        if (num_rep == 8) MMU_FORCES_RB(V, L, 8);                 \
+        else if (num_rep == 4) MMU_FORCES_RB(V, L, 4);            \
+        else MMU_FORCES(V, L);                                    \
+    } while (0)
     switch (dim) {
-        case 2: MMU_FORCES(2, 1); break;
-        case 4: MMU_FORCES(4, 1); break;
-        case 8: MMU_FORCES(4, 2); break;
-        case 16: MMU_FORCES(4, 4); break;
-        case 32: MMU_FORCES(4, 8); break;
-        case 64: MMU_FORCES(4, 16); break;
-        case 128: MMU_FORCES(4, 32); break;
+        case 2: MMU_FORCES_DIM(2, 1); break;
+        case 4: MMU_FORCES_DIM(4, 1); break;
+        case 8: MMU_FORCES_DIM(4, 2); break;
+        case 16: MMU_FORCES_DIM(4, 4); break;
+        case 32: MMU_FORCES_DIM(4, 8); break;
+        case 64: MMU_FORCES_DIM(4, 16); break;
+        case 128: MMU_FORCES_DIM(4, 32); break;
         default:
             edge_forces_generic_kernel<<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept,
                                                                n_batches, batch_size, num_rep, (uint32_t)rep_count,
                                                                head, tail, grad_head, grad_tail, dim, a, b, seed, os, loss);
     }
+#undef MMU_FORCES_DIM
+#undef MMU_FORCES_RB
 #undef MMU_FORCES
     MMU_LAUNCH_CHECK();
     return MMU_OK;
@@ -484,9 +733,22 @@ extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int di
     MMU_CHECK_ARG(dim >= 1 && chunk >= 1 && temperature > 0.f, "mmu_infonce: bad dim/chunk/temperature");
     MMU_CHECK_ARG(num >= 0 && num < ((int64_t)1 << 31), "mmu_infonce: num must be < 2^31");
     if (num == 0) return MMU_OK;
-    infonce_kernel<<<(unsigned)((num + 127) / 128), 128, 0, as_stream(stream)>>>(
-        e0, e1, num, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id,
-        reinterpret_cast<const OptState *>(state), loss);
+    const OptState *os = reinterpret_cast<const OptState *>(state);
+#define MMU_NCE(V, L)                                                                                              \
+    infonce_vec_kernel<V, L><<<(unsigned)((num * L + 255) / 256), 256, 0, as_stream(stream)>>>(                   \
+        e0, e1, num, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id, os, loss)
+    switch (dim) {
+        case 4: MMU_NCE(4, 1); break;
+        case 8: MMU_NCE(4, 2); break;
+        case 16: MMU_NCE(4, 4); break;
+        case 32: MMU_NCE(4, 8); break;
+        case 64: MMU_NCE(4, 16); break;
+        case 128: MMU_NCE(4, 32); break;
+        default:
+            infonce_kernel<<<(unsigned)((num + 127) / 128), 128, 0, as_stream(stream)>>>(
+                e0, e1, num, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id, os, loss);
+    }
+#undef MMU_NCE
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

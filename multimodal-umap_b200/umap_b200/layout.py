@@ -115,6 +115,8 @@ class LayoutOptimizer:
             # consume one draw from the global generator so torch.manual_seed controls the device stream too
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.sample_stream == "device" else 0
         self.seed = int(seed)
+        # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
+        self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
         self.losses: list[float] = []
         self.edge_updates = 0          # host-stream mode counts them exactly; device mode reads kept_count
@@ -127,7 +129,8 @@ class LayoutOptimizer:
         check(lib().mmu_edge_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg),
                                     ptr(batch_kept), mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count,
                                     ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a, self.b,
-                                    self.seed, ptr(self.state), ptr(self.loss), stream()), "mmu_edge_forces")
+                                    self.seed, ptr(self.state), ptr(self.loss), int(self.fast_math), stream()),
+              "mmu_edge_forces")
 
     def _infonce(self, src: _Modality, dst: _Modality, perm, neg, stream_id: int):
         num = min(src.count, dst.count)
