@@ -45,6 +45,9 @@ const char *mmu_last_error(void);
 /* Number of kernels of this library launched by the process so far (every launch site counts
  * itself); bench.py reports the difference over its timed region as "gpu_launches". */
 uint64_t mmu_launch_count(void);
+/* Host code that replays a captured CUDA graph of this library's kernels adds the replayed
+ * kernel launches here (a graph replay does not pass through the launch sites). */
+void mmu_launch_count_add(uint64_t n);
 /* Device properties the host uses to size persistent grids. Synchronous. */
 int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
 

@@ -38,6 +38,8 @@ extern "C" int mmu_abi_version(void) { return MMU_ABI_VERSION; }
 
 extern "C" const char *mmu_last_error(void) { return mmu::g_err; }
 
+extern "C" void mmu_launch_count_add(uint64_t n) { mmu::count_launch((int)n); }
+
 extern "C" uint64_t mmu_launch_count(void) { return __atomic_load_n(&mmu::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes) {

@@ -652,7 +652,7 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     }
     L.n_splits = best_s;
     L.tiles_per_split = (L.n_tiles + L.n_splits - 1) / L.n_splits;
-    L.stat_blocks = (int)((n_db + 511) / 512 < 296 ? (n_db + 511) / 512 : 296);
+    L.stat_blocks = (int)((n_db + 31) / 32 < 296 ? (n_db + 31) / 32 : 296);
     if (L.stat_blocks < 1) L.stat_blocks = 1;
     L.rows_per_stat_block = (int)((n_db + L.stat_blocks - 1) / L.stat_blocks);
     size_t o = 0;
@@ -713,7 +713,7 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     int launches = 1;
     if (!L.shared_operand) {
         // the queries only contribute to the range of the common scale
-        int qb = (int)((n_query + 511) / 512 < 296 ? (n_query + 511) / 512 : 296);
+        int qb = (int)((n_query + 31) / 32 < 296 ? (n_query + 31) / 32 : 296);
         int rpb = (int)((n_query + qb - 1) / qb);
         // the queries' partial sums are not used: they go to the second half of the scratch area
         float *scratch = partial + (size_t)296 * dim;

@@ -183,8 +183,26 @@ class LayoutOptimizer:
             self.loss.zero_()
 
     def run(self, epochs: int):
-        for _ in range(epochs):
-            self.epoch()
+        """`epochs` optimiser epochs.  With the device sample stream an epoch is a fixed sequence of
+        launches whose only varying inputs (epoch counter, Adam step) live in device memory, so it
+        is captured once into a CUDA graph and replayed: one graph launch per epoch instead of a
+        dozen kernel launches (sub-millisecond epochs are launch-latency territory)."""
+        use_graph = (self.sample_stream == "device" and self.loss is None and epochs > 2
+                     and os.environ.get("MMUMAP_GRAPH", "1") == "1")
+        if not use_graph:
+            for _ in range(epochs):
+                self.epoch()
+            return [m.p for m in self.mods]
+        self.epoch()                                   # eager first epoch: loads every kernel before capture
+        graph = torch.cuda.CUDAGraph()
+        before = lib().mmu_launch_count()
+        with torch.cuda.graph(graph):
+            self.epoch()                               # recorded, not executed
+        per_epoch = lib().mmu_launch_count() - before
+        lib().mmu_launch_count_add((epochs - 2) * per_epoch)      # the capture pass itself counted once
+        for _ in range(epochs - 1):
+            graph.replay()
+        self._graph = graph                            # keep alive until the stream has drained
         return [m.p for m in self.mods]
 
     def kept_last_epoch(self) -> int:

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "mmu_abi_version": (c_int, []),
     "mmu_last_error": (ctypes.c_char_p, []),
     "mmu_launch_count": (c_uint64, []),
+    "mmu_launch_count_add": (None, [c_uint64]),
     "mmu_device_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_exact_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
                                   c_int64, c_int, c_void_p, c_void_p, c_void_p]),
