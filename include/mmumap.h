@@ -161,6 +161,14 @@ int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_s
                     uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
                     int32_t *batch_kept, mmu_stream_t stream);
 
+/* The same for the edges [edge_lo, edge_hi) of the COO only (edge-sharded multi-GPU optimisation):
+ * kept_pos holds GLOBAL edge positions and the random stream is keyed on global positions, so the
+ * union over shards equals what mmu_edge_sample draws on one GPU. */
+int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
+                          int batch_size, int n_batches, uint64_t seed, const uint32_t *state,
+                          int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept,
+                          mmu_stream_t stream);
+
 /* K7b: forces of every kept edge and its num_rep negatives, accumulated with red.global.add
  * into the gradient table(s).  Gradient of
  *   mean_batches[ mean_kept log(1+a s^b) + mean_{kept*R} -log(a s^b/(1+a s^b)+1e-6) ],
@@ -191,6 +199,14 @@ int mmu_infonce(const float *e0, const float *e1, int64_t num, int dim, const in
                 const int32_t *neg, int n_neg, int chunk, float weight, float temperature,
                 float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
                 const uint32_t *state, float *loss, mmu_stream_t stream);
+
+/* The same for the anchors [anchor_lo, anchor_hi) of the `num` anchors only (anchor-sharded
+ * multi-GPU optimisation); weights, chunks and the random stream are those of the full range. */
+int mmu_infonce_range(const float *e0, const float *e1, int64_t num, int64_t anchor_lo,
+                      int64_t anchor_hi, int dim, const int32_t *perm, const int32_t *neg, int n_neg,
+                      int chunk, float weight, float temperature, float *grad0, float *grad1,
+                      uint64_t seed, uint32_t stream_id, const uint32_t *state, float *loss,
+                      mmu_stream_t stream);
 
 /* K9: fused Adam update over a dense table (torch.optim.Adam single-tensor semantics,
  * eps=1e-8 style denominator sqrt(v)/bc2_sqrt + eps), reading step_size / bc2_sqrt from

@@ -32,16 +32,18 @@ __global__ void opt_state_advance_kernel(OptState *s, double lr, double beta1, d
 // ------------------------------------------------------------------ K7a: edge sampling
 // thread handles 4 consecutive edges (one Philox call -> 4 uniforms)
 __global__ void __launch_bounds__(256)
-edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w, int64_t nnz, int batch_size,
-                   uint64_t seed, const OptState *__restrict__ st, int32_t *__restrict__ kept_pos,
+edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w, int64_t edge_lo, int64_t nnz,
+                   int batch_size, uint64_t seed, const OptState *__restrict__ st, int32_t *__restrict__ kept_pos,
                    int32_t *__restrict__ kept_count, int32_t *__restrict__ batch_kept) {
+    // edges [edge_lo, nnz) of the global COO; the Philox counter is the GLOBAL quad index, so a
+    // shard draws exactly what the single-GPU run draws for the same edges
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31;
     const int64_t n4 = (nnz + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // all lanes of a warp iterate the same number of times (warp-level collectives below)
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    const int64_t first = (edge_lo >> 2) + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
     for (int64_t wbase = first; wbase < n4; wbase += stride) {
         int64_t q = wbase + lane;
         int32_t pos[4];
@@ -53,7 +55,7 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 int64_t e = q * 4 + i;
-                if (e < nnz && u01(rv[i]) < w[e]) {     // ref: model.py:432  rand < w
+                if (e >= edge_lo && e < nnz && u01(rv[i]) < w[e]) {     // ref: model.py:432  rand < w
                     pos[cnt] = (int32_t)e;
                     brow[cnt] = row[e] / batch_size;
                     ++cnt;
@@ -429,13 +431,13 @@ edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__res
 constexpr int NCE_MAX = 16;   // 1 positive + up to 15 negatives
 
 __global__ void __launch_bounds__(128)
-infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int dim,
+infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int64_t a_lo, int64_t a_hi, int dim,
                const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
                float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
                uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = a_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float loss_local = 0.f;
-    if (t < num) {
+    if (t < a_hi) {
         const int64_t n_chunks = (num + chunk - 1) / chunk;
         const int64_t cidx = t / chunk;
         const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
@@ -513,15 +515,15 @@ infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64
 // red.global.add -- the same closed form as infonce_kernel (ref: model.py:364-394).
 template <int VEC, int LANES>
 __global__ void __launch_bounds__(256)
-infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num,
+infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int64_t a_lo, int64_t a_hi,
                    const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
                    float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
                    uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
     constexpr int DIM = VEC * LANES;
     const int gl = threadIdx.x % LANES;
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const bool active = t < num;
-    const int64_t tt = active ? t : 0;
+    const int64_t t = a_lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const bool active = t < a_hi;
+    const int64_t tt = active ? t : a_lo;
     const int64_t n_chunks = (num + chunk - 1) / chunk;
     const int64_t cidx = tt / chunk;
     const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
@@ -647,25 +649,32 @@ extern "C" int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, d
     return MMU_OK;
 }
 
-extern "C" int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
-                               uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
-                               int32_t *batch_kept, mmu_stream_t stream) {
+extern "C" int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
+                                     int batch_size, int n_batches, uint64_t seed, const uint32_t *state,
+                                     int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(row && w && state && kept_pos && kept_count && batch_kept, "mmu_edge_sample: null pointer");
     MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample: bad batch geometry");
-    MMU_CHECK_ARG(nnz >= 0 && nnz < ((int64_t)1 << 31), "mmu_edge_sample: nnz must be < 2^31");
+    MMU_CHECK_ARG(edge_lo >= 0 && edge_hi >= edge_lo && edge_hi < ((int64_t)1 << 31), "mmu_edge_sample: bad edge range");
     cudaStream_t st = as_stream(stream);
     MMU_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st));
     MMU_CUDA(cudaMemsetAsync(batch_kept, 0, sizeof(int32_t) * (size_t)n_batches, st));
-    if (nnz == 0) return MMU_OK;
-    int64_t n4 = (nnz + 3) / 4;
+    if (edge_hi == edge_lo) return MMU_OK;
+    int64_t n4 = (edge_hi + 3) / 4 - edge_lo / 4;
     int64_t want = (n4 + 255) / 256;
     unsigned cap = persistent_blocks(256, 8);
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
-    edge_sample_kernel<<<blocks, 256, 0, st>>>(row, w, nnz, batch_size, seed, reinterpret_cast<const OptState *>(state),
-                                               kept_pos, kept_count, batch_kept);
+    edge_sample_kernel<<<blocks, 256, 0, st>>>(row, w, edge_lo, edge_hi, batch_size, seed,
+                                               reinterpret_cast<const OptState *>(state), kept_pos, kept_count, batch_kept);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
+}
+
+extern "C" int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
+                               uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
+                               int32_t *batch_kept, mmu_stream_t stream) {
+    return mmu_edge_sample_range(row, w, 0, nnz, batch_size, n_batches, seed, state, kept_pos, kept_count, batch_kept,
+                                 stream);
 }
 
 extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
@@ -723,20 +732,36 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
     return MMU_OK;
 }
 
+extern "C" int mmu_infonce_range(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                                 int dim, const int32_t *perm, const int32_t *neg, int n_neg, int chunk, float weight,
+                                 float temperature, float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                                 const uint32_t *state, float *loss, mmu_stream_t stream);
+
 extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int dim, const int32_t *perm,
                            const int32_t *neg, int n_neg, int chunk, float weight, float temperature, float *grad0,
                            float *grad1, uint64_t seed, uint32_t stream_id, const uint32_t *state, float *loss,
                            mmu_stream_t stream) {
+    return mmu_infonce_range(e0, e1, num, 0, num, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed,
+                             stream_id, state, loss, stream);
+}
+
+extern "C" int mmu_infonce_range(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                                 int dim, const int32_t *perm, const int32_t *neg, int n_neg, int chunk, float weight,
+                                 float temperature, float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                                 const uint32_t *state, float *loss, mmu_stream_t stream) {
     using namespace mmu;
+    MMU_CHECK_ARG(anchor_lo >= 0 && anchor_lo <= anchor_hi && anchor_hi <= num, "mmu_infonce: bad anchor range");
     MMU_CHECK_ARG(e0 && e1 && grad0 && grad1 && state, "mmu_infonce: null pointer");
     MMU_CHECK_ARG(n_neg >= 0 && n_neg < NCE_MAX, "mmu_infonce: n_neg=%d outside [0,%d)", n_neg, NCE_MAX);
     MMU_CHECK_ARG(dim >= 1 && chunk >= 1 && temperature > 0.f, "mmu_infonce: bad dim/chunk/temperature");
     MMU_CHECK_ARG(num >= 0 && num < ((int64_t)1 << 31), "mmu_infonce: num must be < 2^31");
-    if (num == 0) return MMU_OK;
+    if (anchor_hi == anchor_lo) return MMU_OK;
     const OptState *os = reinterpret_cast<const OptState *>(state);
+    const int64_t cnt = anchor_hi - anchor_lo;
 #define MMU_NCE(V, L)                                                                                              \
-    infonce_vec_kernel<V, L><<<(unsigned)((num * L + 255) / 256), 256, 0, as_stream(stream)>>>(                   \
-        e0, e1, num, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id, os, loss)
+    infonce_vec_kernel<V, L><<<(unsigned)((cnt * L + 255) / 256), 256, 0, as_stream(stream)>>>(                   \
+        e0, e1, num, anchor_lo, anchor_hi, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed,       \
+        stream_id, os, loss)
     switch (dim) {
         case 4: MMU_NCE(4, 1); break;
         case 8: MMU_NCE(4, 2); break;
@@ -745,8 +770,9 @@ extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int di
         case 64: MMU_NCE(4, 16); break;
         case 128: MMU_NCE(4, 32); break;
         default:
-            infonce_kernel<<<(unsigned)((num + 127) / 128), 128, 0, as_stream(stream)>>>(
-                e0, e1, num, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed, stream_id, os, loss);
+            infonce_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, as_stream(stream)>>>(
+                e0, e1, num, anchor_lo, anchor_hi, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed,
+                stream_id, os, loss);
     }
 #undef MMU_NCE
     MMU_LAUNCH_CHECK();

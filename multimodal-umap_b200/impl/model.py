@@ -24,6 +24,7 @@ import weakref
 import torch
 
 from umap_b200 import graph as G
+from umap_b200 import dist as D
 from umap_b200 import native, profiler
 from umap_b200.layout import LayoutOptimizer
 from umap_b200.spectral import spectral_init
@@ -120,7 +121,13 @@ class UMAPEncoder:
                 sym = G.fuzzy_union(g.col2d, g.w2d)                      # model.py:271
             graph = _coo(sym)
             with profiler.stage("spectral_init"):
-                embed = self.embed_all(graph)
+                # multi-GPU: modality m is solved by rank m % world and broadcast (embeddings are replicated)
+                owner = self.id % D.world()
+                if D.rank() == owner:
+                    embed = self.embed_all(graph).contiguous()
+                else:
+                    embed = torch.empty((input.shape[0], self.out_dim), dtype=torch.float32, device="cuda")
+                D.broadcast(embed, owner)
         elif mode == "transform":
             embed = self.embed_query(ref_embeds, graph)
         else:

@@ -12,6 +12,7 @@ from dataclasses import dataclass
 
 import torch
 
+from . import dist as D
 from . import native, profiler
 from .native import check, lib, ptr, stream
 
@@ -107,18 +108,24 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         raise ValueError(f"k_neighbors={k} exceeds the supported maximum {native.MAX_K}")
     if db.shape[0] - (1 if exclude_self else 0) < k:
         raise ValueError(f"need more than k={k} candidate points per row, got {db.shape[0]}")
-    flops = 2.0 * query.shape[0] * db.shape[0] * db.shape[1]
-    if method == "simt":
-        with profiler.stage("knn", flops=flops, kernel="knn_exact_f32_kernel"):
-            return knn_exact_simt(query, db, k, exclude_self)
-    if method == "tc":
-        if k > native.KNN_TC_MAX_K:            # the per-row candidate lists hold 64 entries
-            with profiler.stage("knn", flops=flops, kernel="knn_exact_f32_kernel"):
-                return knn_exact_simt(query, db, k, exclude_self)
-        from .knn_tc import knn_tc
-        with profiler.stage("knn", flops=flops, kernel="knn_tc"):
-            return knn_tc(query, db, k, exclude_self)
-    raise ValueError(f"unknown kNN method {method!r}")
+    use_tc = method == "tc" and k <= native.KNN_TC_MAX_K          # the per-row candidate lists hold 64 entries
+    if method not in ("tc", "simt"):
+        raise ValueError(f"unknown kNN method {method!r}")
+
+    def search(q, d, kk, excl, q_base):
+        if use_tc:
+            from .knn_tc import knn_tc
+            return knn_tc(q, d, kk, excl, query_base=q_base)
+        return knn_exact_simt(q, d, kk, excl, query_base=q_base)
+
+    kernel = "knn_tc" if use_tc else "knn_exact_f32_kernel"
+    if D.world() > 1 and query is db:
+        # multi-GPU fit: query row-blocks per rank, all-gather of the per-row results
+        lo, hi = D.row_block(db.shape[0], D.rank(), D.world())
+        with profiler.stage("knn", flops=2.0 * (hi - lo) * db.shape[0] * db.shape[1], kernel=kernel):
+            return D.knn_sharded_rows(_f32c(db), k, exclude_self, search)
+    with profiler.stage("knn", flops=2.0 * query.shape[0] * db.shape[0] * db.shape[1], kernel=kernel):
+        return search(query, db, k, exclude_self, 0)
 
 
 def smooth_knn(idx: torch.Tensor, dist: torch.Tensor, solver: str = "bisect", n_iter: int | None = None):

@@ -17,6 +17,7 @@ import os
 
 import torch
 
+from . import dist as D
 from . import native
 from .graph import Graph
 from .native import check, lib, ptr, stream
@@ -34,12 +35,12 @@ def default_stream() -> str:
 class _Modality:
     """Device state of one table being optimised."""
 
-    def __init__(self, embed: torch.Tensor, graph: Graph, batch_size: int, ref: torch.Tensor | None):
+    def __init__(self, embed: torch.Tensor, graph: Graph, batch_size: int, ref: torch.Tensor | None, flat, offset: int):
         dev = torch.device("cuda")
-        self.p = embed.detach().to(dev, torch.float32).contiguous().clone()
-        self.g = torch.zeros_like(self.p)
-        self.m = torch.zeros_like(self.p)
-        self.v = torch.zeros_like(self.p)
+        n, d = embed.shape
+        # p/g/m/v of all modalities live in four flat buffers: one all-reduce and one Adam launch per epoch
+        self.p, self.g, self.m, self.v = (f[offset:offset + n * d].view(n, d) for f in flat)
+        self.p.copy_(embed.detach().to(dev, torch.float32))
         self.graph = graph
         self.ref = None if ref is None else ref.detach().to(dev, torch.float32).contiguous()
         self.count = self.p.shape[0]
@@ -47,9 +48,18 @@ class _Modality:
         self.batch_size = batch_size
         self.n_batches = (self.count + batch_size - 1) // batch_size
         self.rep_count = self.ref.shape[0] if self.ref is not None else self.count
-        self.kept_pos = torch.empty(max(graph.nnz, 1), dtype=torch.int32, device=dev)
         self.kept_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.batch_kept = torch.zeros(self.n_batches, dtype=torch.int32, device=dev)
+        # multi-GPU: this rank owns a range of row-batches, i.e. a contiguous range of edges
+        w, r = D.world(), D.rank()
+        self.b_lo, self.b_hi = D.batch_range(self.n_batches, r, w)
+        if w == 1:
+            self.e_lo, self.e_hi = 0, graph.nnz
+        else:
+            lo_row = min(self.b_lo * batch_size, self.count)
+            hi_row = min(self.b_hi * batch_size, self.count)
+            self.e_lo, self.e_hi = (int(v) for v in graph.rowptr[[lo_row, hi_row]].tolist())
+        self.kept_pos = torch.empty(max(self.e_hi - self.e_lo, 1), dtype=torch.int32, device=dev)
         # host copies for the replayed stream
         self._w_cpu = None
         self._rowptr_cpu = None
@@ -76,9 +86,15 @@ def replay_host_draws(mod: _Modality, num_rep: int):
         kept_chunks.append(pos)
         neg_chunks.append(neg)
         counts.append(num_pairs)
+    counts_t = torch.tensor(counts, dtype=torch.int32)
+    if D.world() > 1:
+        # every rank replays the whole stream (same generator state everywhere) and keeps its batches
+        keep = range(mod.b_lo, mod.b_hi)
+        kept_chunks = [kept_chunks[b] for b in keep] or [torch.zeros(0, dtype=torch.int64)]
+        neg_chunks = [neg_chunks[b] for b in keep] or [torch.zeros((0, num_rep), dtype=torch.int64)]
     kept = torch.cat(kept_chunks).to(torch.int32)
     neg = torch.cat(neg_chunks).to(torch.int32).reshape(-1, num_rep)
-    return kept, neg, torch.tensor(counts, dtype=torch.int32)
+    return kept, neg, counts_t
 
 
 def replay_infonce_draws(num: int):
@@ -103,18 +119,23 @@ class LayoutOptimizer:
         self.sample_stream = sample_stream or default_stream()
         if self.sample_stream not in ("host", "device"):
             raise ValueError(f"unknown sample stream {self.sample_stream!r}")
-        self.mods = [
-            _Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
-                      None if refs is None else refs[i])
-            for i, (e, g) in enumerate(zip(embeds, graphs))
-        ]
         dev = torch.device("cuda")
+        # every table starts on a 256-byte boundary of the flat buffers (vector loads / red.v4)
+        sizes = [-(-(int(e.shape[0]) * int(e.shape[1])) // 64) * 64 for e in embeds]
+        total = sum(sizes)
+        self.flat = tuple(torch.zeros(max(total, 1), dtype=torch.float32, device=dev) for _ in range(4))   # p, g, m, v
+        self.total = total
+        self.mods, off = [], 0
+        for i, (e, g) in enumerate(zip(embeds, graphs)):
+            self.mods.append(_Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
+                                       None if refs is None else refs[i], self.flat, off))
+            off += sizes[i]
         self.state = torch.zeros(native.OPT_STATE_WORDS, dtype=torch.int32, device=dev)
         check(lib().mmu_opt_state_init(ptr(self.state), stream()), "mmu_opt_state_init")
         if seed is None:
             # consume one draw from the global generator so torch.manual_seed controls the device stream too
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.sample_stream == "device" else 0
-        self.seed = int(seed)
+        self.seed = D.same_on_all_ranks(int(seed))
         # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
         self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
@@ -134,9 +155,10 @@ class LayoutOptimizer:
 
     def _infonce(self, src: _Modality, dst: _Modality, perm, neg, stream_id: int):
         num = min(src.count, dst.count)
-        check(lib().mmu_infonce(ptr(src.p), ptr(dst.p), num, src.dim, ptr(perm), ptr(neg), INFONCE_NEG,
-                                INFONCE_CHUNK, self.alpha, INFONCE_TAU, ptr(src.g), ptr(dst.g), self.seed,
-                                stream_id, ptr(self.state), ptr(self.loss), stream()), "mmu_infonce")
+        a_lo, a_hi = D.item_range(num, D.rank(), D.world())
+        check(lib().mmu_infonce_range(ptr(src.p), ptr(dst.p), num, a_lo, a_hi, src.dim, ptr(perm), ptr(neg), INFONCE_NEG,
+                                      INFONCE_CHUNK, self.alpha, INFONCE_TAU, ptr(src.g), ptr(dst.g), self.seed,
+                                      stream_id, ptr(self.state), ptr(self.loss), stream()), "mmu_infonce_range")
 
     def epoch(self):
         host = self.sample_stream == "host"
@@ -153,9 +175,10 @@ class LayoutOptimizer:
                 self._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
             else:
                 g = mod.graph
-                check(lib().mmu_edge_sample(ptr(g.row), ptr(g.val), g.nnz, mod.batch_size, mod.n_batches, self.seed,
-                                            ptr(self.state), ptr(mod.kept_pos), ptr(mod.kept_count),
-                                            ptr(mod.batch_kept), stream()), "mmu_edge_sample")
+                check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
+                                                  mod.n_batches, self.seed, ptr(self.state), ptr(mod.kept_pos),
+                                                  ptr(mod.kept_count), ptr(mod.batch_kept), stream()),
+                      "mmu_edge_sample_range")
                 self._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
         if self.mode == "fit":                                           # model.py:459-472
             n = len(self.mods)
@@ -174,11 +197,14 @@ class LayoutOptimizer:
                         else:
                             self._infonce(self.mods[s], self.mods[t], None, None, sid)
                         sid += 1
+        # multi-GPU: one all-reduce of the flat gradient buffer, then the identical Adam step everywhere
+        D.all_reduce_sum(self.flat[1])
         check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
-        for mod in self.mods:
-            check(lib().mmu_adam_step(ptr(mod.p), ptr(mod.g), ptr(mod.m), ptr(mod.v), mod.p.numel(), BETA1, BETA2,
-                                      EPS, ptr(self.state), 1, stream()), "mmu_adam_step")
+        p, g, m, v = self.flat
+        check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
+                                  stream()), "mmu_adam_step")
         if self.loss is not None:
+            D.all_reduce_sum(self.loss)
             self.losses.append(float(self.loss.item()))
             self.loss.zero_()
 
@@ -188,11 +214,12 @@ class LayoutOptimizer:
         is captured once into a CUDA graph and replayed: one graph launch per epoch instead of a
         dozen kernel launches (sub-millisecond epochs are launch-latency territory)."""
         use_graph = (self.sample_stream == "device" and self.loss is None and epochs > 2
-                     and os.environ.get("MMUMAP_GRAPH", "1") == "1")
+                     and os.environ.get("MMUMAP_GRAPH", "1") == "1"
+                     and (D.world() == 1 or os.environ.get("MMUMAP_GRAPH_NCCL", "1") == "1"))
         if not use_graph:
             for _ in range(epochs):
                 self.epoch()
-            return [m.p for m in self.mods]
+            return self.result()
         self.epoch()                                   # eager first epoch: loads every kernel before capture
         graph = torch.cuda.CUDAGraph()
         before = lib().mmu_launch_count()
@@ -203,7 +230,13 @@ class LayoutOptimizer:
         for _ in range(epochs - 1):
             graph.replay()
         self._graph = graph                            # keep alive until the stream has drained
-        return [m.p for m in self.mods]
+        return self.result()
+
+    def result(self):
+        return [m.p.clone() for m in self.mods]
 
     def kept_last_epoch(self) -> int:
-        return int(sum(int(m.kept_count.item()) for m in self.mods))
+        """Kept edges of the last epoch over all ranks."""
+        t = torch.stack([m.kept_count[0] for m in self.mods]).sum().to(torch.int64).reshape(1)
+        D.all_reduce_sum(t)
+        return int(t.item())

@@ -50,11 +50,15 @@ _SIGNATURES = {
     "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
     "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "mmu_edge_sample_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_void_p, c_int, c_void_p]),
     "mmu_infonce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                             c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "mmu_infonce_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
+                                  c_float, c_float, c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
     "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p,
                               c_int, c_void_p]),
 }

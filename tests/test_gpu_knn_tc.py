@@ -108,3 +108,31 @@ def test_matches_exhaustive_cuda_kernel_at_scale(n, d, kind):
     si, sd = G.knn_exact_simt(x, x, 15, True)
     _same(ti, td, si.cpu().numpy(), sd.cpu().numpy())
     assert st["fallback_rows"] <= 0.02 * n, st
+
+
+def test_database_ring_emulated_on_one_gpu():
+    """The row-sharded-database search (umap_b200.dist.ring_knn's per-shard step): searching the
+    database shard by shard with mmu_knn_tc and merging with mmu_knn_merge equals the one-shot
+    search, including self-exclusion in the shard that holds the query rows."""
+    from umap_b200 import knn_tc
+    from umap_b200.native import check, lib, ptr, stream
+    x = _blobs(3000, 64, 6, 21)
+    xt = torch.from_numpy(x).cuda()
+    k, shards = 15, [(0, 1024), (1024, 2048), (2048, 3000)]
+    q_lo, q_hi = 1024, 2048
+    q = xt[q_lo:q_hi].contiguous()
+    best = None
+    for lo, hi in shards:
+        same = lo == q_lo
+        i_s, d_s = knn_tc.knn_tc(q, xt[lo:hi].contiguous(), k, same, query_base=0)
+        i_s = torch.where(i_s >= 0, i_s + lo, i_s)
+        if best is None:
+            best = (i_s, d_s)
+        else:
+            oi = torch.empty_like(i_s)
+            od = torch.empty_like(d_s)
+            check(lib().mmu_knn_merge(ptr(best[0]), ptr(best[1]), ptr(i_s), ptr(d_s), q.shape[0], k, ptr(oi), ptr(od),
+                                      stream()), "merge")
+            best = (oi, od)
+    oi, od = orc.knn_exact(x, x, k, True)
+    _same(best[0].cpu().numpy(), best[1].cpu().numpy(), oi[q_lo:q_hi], od[q_lo:q_hi])

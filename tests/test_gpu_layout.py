@@ -259,3 +259,51 @@ def test_device_stream_fit_reaches_reference_quality(golden_dir):
     lh, ld = np.array(oh.losses), np.array(od.losses)
     assert np.all(np.isfinite(ld))
     assert abs(lh[-10:].mean() - ld[-10:].mean()) < 0.05 * abs(lh[-10:].mean())
+
+
+def test_edge_and_anchor_ranges_partition_the_single_gpu_stream():
+    """Multi-GPU sharding contract on one device: sampling edge ranges [0,a),[a,b),[b,nnz) keeps
+    exactly the edges the full-range call keeps (Philox keyed on global positions), and the InfoNCE
+    gradients of anchor ranges add up to the full-range gradient."""
+    from umap_b200.native import check, lib, ptr, stream
+    rng = np.random.default_rng(11)
+    n, k, bs = 5000, 15, 256
+    rows = torch.from_numpy(np.repeat(np.arange(n, dtype=np.int32), k)).cuda()
+    w = torch.from_numpy(rng.random(n * k).astype(np.float32)).cuda()
+    nnz, nb = n * k, (n + bs - 1) // bs
+    state = torch.zeros(8, dtype=torch.int32, device="cuda")
+    check(lib().mmu_opt_state_init(ptr(state), stream()), "init")
+
+    def sample(lo, hi):
+        kept = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        bk = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        check(lib().mmu_edge_sample_range(ptr(rows), ptr(w), lo, hi, bs, nb, 99, ptr(state), ptr(kept), ptr(cnt), ptr(bk),
+                                          stream()), "sample_range")
+        return np.sort(kept[: int(cnt.item())].cpu().numpy()), bk.cpu().numpy()
+
+    full, bk_full = sample(0, nnz)
+    cuts = [0, 1001, 40007, nnz]                      # deliberately not multiples of 4
+    parts = [sample(a, b) for a, b in zip(cuts, cuts[1:])]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), full)
+    assert np.array_equal(sum(p[1] for p in parts), bk_full)
+    for (a, b), (kp, _) in zip(zip(cuts, cuts[1:]), parts):
+        assert kp.size == 0 or (kp.min() >= a and kp.max() < b)
+
+    dim, num = 16, 3300
+    e0 = torch.from_numpy(rng.standard_normal((num, dim)).astype(np.float32)).cuda()
+    e1 = torch.from_numpy(rng.standard_normal((num + 50, dim)).astype(np.float32)).cuda()
+
+    def nce(lo, hi):
+        g0, g1 = torch.zeros_like(e0), torch.zeros_like(e1)
+        loss = torch.zeros(1, device="cuda")
+        check(lib().mmu_infonce_range(ptr(e0), ptr(e1), num, lo, hi, dim, None, None, 9, 1000, 1.0, 0.5, ptr(g0), ptr(g1),
+                                      7, 0, ptr(state), ptr(loss), stream()), "infonce_range")
+        return g0.cpu().numpy().astype(np.float64), g1.cpu().numpy().astype(np.float64), float(loss.item())
+
+    f0, f1, fl = nce(0, num)
+    a0, a1, al = nce(0, 1234)
+    b0, b1, bl = nce(1234, num)
+    assert np.abs(a0 + b0 - f0).max() < 1e-6 * np.abs(f0).max()
+    assert np.abs(a1 + b1 - f1).max() < 2e-6 * np.abs(f1).max()
+    assert abs(al + bl - fl) < 1e-5 * abs(fl)
