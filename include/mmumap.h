@@ -139,6 +139,12 @@ int mmu_embed_query(const int32_t *col, const float *w, int64_t n_rows, int k, c
 int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                  const float *x, int m, float *y, mmu_stream_t stream);
 
+/* y = alpha * (A x) + beta * x + gamma * z  (z nullable; z may alias y): one three-term
+ * Chebyshev recurrence step of the spectral initialisation per launch.  ref: model.py:221-234 */
+int mmu_spmm_csr_axpby(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                       const float *x, int m, float alpha, float beta, const float *z, float gamma,
+                       float *y, mmu_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * K7/K8/K9  layout optimiser               ref: model.py:396-481 (_train),
  *           :312-334 (attractive / repulsive terms), :364-394 (InfoNCE), :403,:474-476 (Adam)

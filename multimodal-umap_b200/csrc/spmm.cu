@@ -30,7 +30,8 @@ embed_query_kernel(const int32_t *__restrict__ col, const float *__restrict__ w,
 __global__ void __launch_bounds__(256)
 spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                 const float *__restrict__ val, int64_t n, const float *__restrict__ x, int m,
-                float *__restrict__ y) {
+                float alpha, float beta, const float *__restrict__ z, float gamma, float *__restrict__ y) {
+    // y = alpha * (A x) + beta * x + gamma * z   (z nullable): one Chebyshev step per launch
     const int lane = threadIdx.x & 31;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
@@ -49,7 +50,12 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
                 if (c < m) acc = fmaf(vv, x[(int64_t)cc * m + c], acc);
             }
         }
-        if (c < m) y[r * m + c] = acc;
+        if (c < m) {
+            float out = alpha * acc;
+            if (beta != 0.f) out = fmaf(beta, x[r * m + c], out);
+            if (z) out = fmaf(gamma, z[r * m + c], out);
+            y[r * m + c] = out;
+        }
     }
 }
 
@@ -74,7 +80,22 @@ extern "C" int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const flo
     MMU_CHECK_ARG(m >= 1, "mmu_spmm_csr: bad m");
     MMU_CHECK_ARG(x != y, "mmu_spmm_csr: x and y must not alias");
     if (n == 0) return MMU_OK;
-    spmm_csr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, m, y);
+    spmm_csr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, m, 1.f, 0.f,
+                                                                                     nullptr, 0.f, y);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_spmm_csr_axpby(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
+                                  const float *x, int m, float alpha, float beta, const float *z, float gamma,
+                                  float *y, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(rowptr && col && val && x && y, "mmu_spmm_csr_axpby: null pointer");
+    MMU_CHECK_ARG(m >= 1, "mmu_spmm_csr_axpby: bad m");
+    MMU_CHECK_ARG(x != y, "mmu_spmm_csr_axpby: x and y must not alias");
+    if (n == 0) return MMU_OK;
+    spmm_csr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, m, alpha,
+                                                                                     beta, z, gamma, y);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

@@ -187,3 +187,13 @@ def spmm(g: Graph, x: torch.Tensor, val: torch.Tensor | None = None) -> torch.Te
     check(lib().mmu_spmm_csr(ptr(g.rowptr), ptr(g.col), ptr(v), g.n_rows, ptr(x), x.shape[1], ptr(y), stream()),
           "mmu_spmm_csr")
     return y
+
+
+def spmm_axpby(g: Graph, val: torch.Tensor, x: torch.Tensor, alpha: float, beta: float, z: torch.Tensor | None,
+               gamma: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = alpha * (A x) + beta * x + gamma * z with A = (g pattern, val); z may be `out`."""
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().mmu_spmm_csr_axpby(ptr(g.rowptr), ptr(g.col), ptr(val), g.n_rows, ptr(x), x.shape[1], float(alpha),
+                                   float(beta), ptr(z), float(gamma), ptr(out), stream()), "mmu_spmm_csr_axpby")
+    return out

@@ -213,9 +213,11 @@ class LayoutOptimizer:
         launches whose only varying inputs (epoch counter, Adam step) live in device memory, so it
         is captured once into a CUDA graph and replayed: one graph launch per epoch instead of a
         dozen kernel launches (sub-millisecond epochs are launch-latency territory)."""
+        mode = os.environ.get("MMUMAP_GRAPH", "auto")
+        small = sum(m.graph.nnz for m in self.mods) <= 1_000_000        # epochs of a few tens of microseconds
         use_graph = (self.sample_stream == "device" and self.loss is None and epochs > 2
-                     and os.environ.get("MMUMAP_GRAPH", "1") == "1"
-                     and (D.world() == 1 or os.environ.get("MMUMAP_GRAPH_NCCL", "1") == "1"))
+                     and (mode == "1" or (mode == "auto" and small))
+                     and (D.world() == 1 or os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1"))
         if not use_graph:
             for _ in range(epochs):
                 self.epoch()
@@ -223,8 +225,18 @@ class LayoutOptimizer:
         self.epoch()                                   # eager first epoch: loads every kernel before capture
         graph = torch.cuda.CUDAGraph()
         before = lib().mmu_launch_count()
-        with torch.cuda.graph(graph):
-            self.epoch()                               # recorded, not executed
+        # plain capture_begin/end on a side stream: the torch.cuda.graph() context manager also runs
+        # gc.collect() and empty_cache(), which costs more than the launches it saves
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                self.epoch()                           # recorded, not executed
+            finally:
+                graph.capture_end()
+        cur.wait_stream(side)
         per_epoch = lib().mmu_launch_count() - before
         lib().mmu_launch_count_add((epochs - 2) * per_epoch)      # the capture pass itself counted once
         for _ in range(epochs - 1):

@@ -14,7 +14,7 @@ import os
 
 import torch
 
-from .graph import Graph, spmm
+from .graph import Graph, spmm, spmm_axpby
 
 
 def normalized_adjacency(g: Graph) -> torch.Tensor:
@@ -70,12 +70,88 @@ def spectral_subspace(g: Graph, out_dim: int, iters: int = 40, degree: int = 8, 
     return v[:, 1:].contiguous()
 
 
+def _gram(x: torch.Tensor, y: torch.Tensor, chunk: int = 256) -> torch.Tensor:
+    """x^T y for tall-skinny [n_pad, b] blocks (n_pad a multiple of `chunk`) as one batched GEMM
+    over row chunks + a reduction: cuBLAS' large-k sgemm is ~20x slower on this shape."""
+    c = x.shape[0] // chunk
+    return torch.bmm(x.view(c, chunk, x.shape[1]).transpose(1, 2), y.view(c, chunk, y.shape[1])).sum(0)
+
+
+def _orthonormalise(x: torch.Tensor) -> torch.Tensor:
+    """SVQB: x (x^T x)^-1/2 through a small symmetric eigendecomposition (no host sync, tolerant of
+    nearly dependent columns, which the Chebyshev filter produces by design)."""
+    gm = _gram(x, x)
+    gm = 0.5 * (gm + gm.T)
+    lam, v = torch.linalg.eigh(gm)
+    lam = lam.clamp(min=lam.max() * 1e-10)
+    return x @ (v * lam.rsqrt())
+
+
+def spectral_chebfsi(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 30, degree: int = 10) -> torch.Tensor:
+    """Chebyshev-filtered subspace iteration (Zhou-Saad) for the out_dim+1 largest eigenpairs of
+    A = D^-1/2 S D^-1/2, i.e. the smallest of the reference's L = I - A + 1e-6 I (model.py:221-230),
+    on the engine's own kernels: one fused SpMM launch per Chebyshev step (mmu_spmm_csr_axpby),
+    batched-GEMM Gram matrices, 32x32 dense eigenproblems.  Stops when every wanted Ritz pair has
+    |A x - theta x| < tol (torch.lobpcg's default tolerance is sqrt(eps_fp32) = 3.5e-4).  Same
+    output contract as embed_all: unit-norm columns, first (trivial) vector dropped, unscaled."""
+    n, dev = g.n_rows, g.val.device
+    m = out_dim + 1
+    b = 32 if m <= 24 else -(-(m + 8) // 4) * 4
+    n_pad = -(-n // 256) * 256
+    aval = normalized_adjacency(g)
+    x = torch.zeros((n_pad, b), dtype=torch.float32, device=dev)
+    x[:n] = torch.randn((n, b), dtype=torch.float32, device=dev)
+    deg = torch.zeros(n, dtype=torch.float32, device=dev)
+    deg.index_add_(0, g.row.long(), g.val)
+    x[:n, 0] = deg.clamp(min=1e-6).sqrt()                    # the known top eigenvector of A
+    x = _orthonormalise(x)
+    ax = torch.zeros_like(x)
+    y0 = torch.zeros_like(x)
+    y1 = torch.zeros_like(x)
+    cut = 0.0
+    for it in range(max_iter):
+        spmm_axpby(g, aval, x, 1.0, 0.0, None, 0.0, out=ax)
+        h = _gram(x, ax)
+        theta, v = torch.linalg.eigh(0.5 * (h + h.T))
+        order = torch.argsort(theta, descending=True)
+        theta, v = theta[order], v[:, order]
+        x = x @ v
+        ax = ax @ v
+        res = (ax[:, :m] - x[:, :m] * theta[:m]).norm(dim=0).max()
+        lo = float(theta[b - 1])
+        if os.environ.get("MMUMAP_SPECTRAL_DEBUG") == "1":
+            print(f"  chebfsi it={it} res={float(res):.3e} theta[0]={float(theta[0]):.6f} theta[m-1]={float(theta[m-1]):.6f} "
+                  f"theta[b-1]={lo:.6f} cut={cut:.4f}")
+        if float(res) < tol or it == max_iter - 1:
+            break
+        # damp [-1, cut].  The classical choice is the smallest Ritz value of the block (-> lambda_b from
+        # below); when a cluster of (near-)equal eigenvalues is wider than the block -- UMAP graphs of
+        # well separated clusters have one eigenvalue ~1 per cluster -- that value runs into the wanted
+        # ones and the filter stops filtering, so the edge is kept a fixed distance below them
+        cut = max(min(lo, float(theta[m - 1]) - 0.05), -0.5)
+        e, c = (cut + 1.0) / 2.0, (cut - 1.0) / 2.0
+        spmm_axpby(g, aval, x, 1.0 / e, -c / e, None, 0.0, out=y1)           # T_1
+        y0.copy_(x)
+        for _ in range(2, degree + 1):
+            spmm_axpby(g, aval, y1, 2.0 / e, -2.0 * c / e, y0, -1.0, out=y0)  # T_k -> overwrites T_{k-2}
+            y0, y1 = y1, y0
+        # the block holds Ritz vectors, so the filtered columns p(A) x_j stay nearly orthogonal and differ
+        # mainly in length (p(theta_j) spans orders of magnitude): equalise the lengths first, otherwise
+        # the fp32 Gram matrix loses the weakly amplified (wanted, slowly converging) directions
+        y1 = y1 / y1.norm(dim=0, keepdim=True).clamp(min=1e-30)
+        x = _orthonormalise(_orthonormalise(y1))
+    vecs = x[:n, 1:m]
+    return (vecs / vecs.norm(dim=0, keepdim=True)).contiguous()
+
+
 def spectral_init(g: Graph, out_dim: int, method: str | None = None) -> torch.Tensor:
-    method = method or os.environ.get("MMUMAP_SPECTRAL", "lobpcg")
+    method = method or os.environ.get("MMUMAP_SPECTRAL", "chebfsi")
     if g.n_rows < 3 * (out_dim + 1):
         raise ValueError(f"spectral init needs at least {3 * (out_dim + 1)} points for out_dim={out_dim}")
     if method == "lobpcg":
         return spectral_lobpcg(g, out_dim)
+    if method == "chebfsi":
+        return spectral_chebfsi(g, out_dim)
     if method == "subspace":
         return spectral_subspace(g, out_dim)
     raise ValueError(f"unknown spectral method {method!r}")
