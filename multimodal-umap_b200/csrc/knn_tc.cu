@@ -426,13 +426,25 @@ struct RsParams {
     int32_t *fallback_rows;
 };
 
-constexpr int RS_WARPS = 8;
-constexpr int RS_TS = 33;    // tile row stride (floats): conflict-free transposed access
+constexpr int RS_WARPS = 4;
+constexpr int RS_TS = 33;    // tile row stride (floats): conflict-free transposed access (scalar path)
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool VEC4>
 __global__ void __launch_bounds__(RS_WARPS * 32)
 knn_tc_rescore_kernel(const RsParams p) {
-    __shared__ float s_tile[RS_WARPS][32 * RS_TS];
+    // two tiles per warp: [32 candidates][32 floats], 16-byte chunks XOR-swizzled by the candidate
+    // number (VEC4 path, cp.async double buffering) -- or one padded transposed tile (scalar path)
+    __shared__ __align__(16) float s_tile[RS_WARPS][2 * 32 * 32 + 64];
     __shared__ int32_t s_p[RS_WARPS][RS_PMAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * RS_WARPS + warp;
@@ -534,38 +546,69 @@ knn_tc_rescore_kernel(const RsParams p) {
         const int my = g * 32 + lane;
         const int32_t my_j = my < np ? s_p[warp][my] : -1;
         float acc = 0.f;
-        for (int tb = 0; tb < p.dim; tb += 32) {
-            const float xv = (tb + lane < p.dim) ? xq[tb + lane] : 0.f;
-            __syncwarp();
-            if (VEC4) {
-                // 8 lanes fetch one candidate's 32 floats (128 B); 4 candidates per instruction
-                const int part = lane & 7;
+        if (VEC4) {
+            // Each candidate row is streamed in 128-byte pieces (8 lanes x 16 B, 4 candidates per
+            // instruction) with cp.async into tile[buf][cand][chunk ^ (cand & 7)]; chunk n+1 is in flight
+            // while chunk n is consumed; lane c then walks candidate c's 32 floats in order with
+            // conflict-free 16-byte shared loads.  The query chunk rides in the same group.
+            const int part = lane & 7;
+            int32_t cjs[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const int c = rr * 4 + (lane >> 3);
+                cjs[rr] = g * 32 + c < np ? s_p[warp][g * 32 + c] : -1;
+            }
+            float *xs = tile + 2 * 32 * 32;                                    // [2][32] query chunk
+            auto issue = [&](int buf, int tb) {
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     const int c = rr * 4 + (lane >> 3);
-                    const int cj = g * 32 + c < np ? s_p[warp][g * 32 + c] : -1;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cj >= 0 && tb + part * 4 < p.dim)
-                        v = __ldg(reinterpret_cast<const float4 *>(p.db + (int64_t)cj * p.dim + tb + part * 4));
-                    tile[(part * 4 + 0) * RS_TS + c] = v.x;
-                    tile[(part * 4 + 1) * RS_TS + c] = v.y;
-                    tile[(part * 4 + 2) * RS_TS + c] = v.z;
-                    tile[(part * 4 + 3) * RS_TS + c] = v.w;
+                    float *dst = tile + buf * 1024 + c * 32 + ((part ^ (c & 7)) << 2);
+                    if (cjs[rr] >= 0 && tb + part * 4 < p.dim)
+                        cp_async16(dst, p.db + (int64_t)cjs[rr] * p.dim + tb + part * 4);
+                    else
+                        *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            } else {
+                if (tb + lane < p.dim) cp_async4(xs + buf * 32 + lane, xq + tb + lane);
+                else xs[buf * 32 + lane] = 0.f;
+                cp_async_commit();
+            };
+            __syncwarp();
+            issue(0, 0);
+            int buf = 0;
+            for (int tb = 0; tb < p.dim; tb += 32, buf ^= 1) {
+                if (tb + 32 < p.dim) { issue(buf ^ 1, tb + 32); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncwarp();
+                const float *row = tile + buf * 1024 + lane * 32;
+#pragma unroll
+                for (int pc = 0; pc < 8; ++pc) {
+                    const float4 y = *reinterpret_cast<const float4 *>(row + ((pc ^ (lane & 7)) << 2));
+                    const float4 x = *reinterpret_cast<const float4 *>(xs + buf * 32 + pc * 4);
+                    float d0 = x.x - y.x; acc = fmaf(d0, d0, acc);     // zero padding beyond dim adds exactly 0
+                    float d1 = x.y - y.y; acc = fmaf(d1, d1, acc);
+                    float d2 = x.z - y.z; acc = fmaf(d2, d2, acc);
+                    float d3 = x.w - y.w; acc = fmaf(d3, d3, acc);
+                }
+                __syncwarp();
+            }
+        } else {
+            for (int tb = 0; tb < p.dim; tb += 32) {
+                const float xv = (tb + lane < p.dim) ? xq[tb + lane] : 0.f;
+                __syncwarp();
                 for (int c = 0; c < 32; ++c) {
                     const int cj = g * 32 + c < np ? s_p[warp][g * 32 + c] : -1;
                     float v = 0.f;
                     if (cj >= 0 && tb + lane < p.dim) v = __ldg(p.db + (int64_t)cj * p.dim + tb + lane);
                     tile[lane * RS_TS + c] = v;
                 }
-            }
-            __syncwarp();
-            const int tn = min(32, p.dim - tb);
-            for (int t = 0; t < tn; ++t) {
-                const float x = __shfl_sync(0xffffffffu, xv, t);
-                const float diff = x - tile[t * RS_TS + lane];
-                acc = fmaf(diff, diff, acc);
+                __syncwarp();
+                const int tn = min(32, p.dim - tb);
+                for (int t = 0; t < tn; ++t) {
+                    const float x = __shfl_sync(0xffffffffu, xv, t);
+                    const float diff = x - tile[t * RS_TS + lane];
+                    acc = fmaf(diff, diff, acc);
+                }
             }
         }
         if (my_j >= 0) keys[g] = dist_key(sqrtf(acc), my_j);

@@ -1,0 +1,23 @@
+"""Seeded two-modality problem shared by oracle/make_golden_e2e.py (reference run) and
+tests/test_gpu_e2e.py (engine run).  TEST INFRASTRUCTURE, NOT PRODUCT CODE."""
+import numpy as np
+
+# reference CLI defaults (main.py:13-24) except the small latent size
+CFG = dict(k_neighbors=15, out_dim=8, min_dist=0.1, train_epochs=600, num_rep=8, lr=0.01, alpha=1.0,
+           batch_size=256, test_epochs=120)
+
+
+def make_problem(n_train: int = 1500, n_test: int = 300, clusters: int = 12, seed: int = 2024):
+    """Paired rows: row i of "texts" and row i of "images" share a cluster and a latent position.
+    Dict order is texts, images (dataset.py:60-63)."""
+    rng = np.random.default_rng(seed)
+    n = n_train + n_test
+    lab = rng.integers(0, clusters, n)
+    z = rng.standard_normal((clusters, 6))[lab] * 3.0 + rng.standard_normal((n, 6))      # shared latent
+    wt = rng.standard_normal((6, 48)) / np.sqrt(6)
+    wi = rng.standard_normal((6, 64)) / np.sqrt(6)
+    texts = np.tanh(0.5 * (z @ wt) + 0.1 * rng.standard_normal((n, 48))).astype(np.float32)
+    images = (2.0 * (z @ wi) + 0.5 * rng.standard_normal((n, 64))).astype(np.float32)
+    train = {"texts": texts[:n_train].copy(), "images": images[:n_train].copy()}
+    test = {"texts": texts[n_train:].copy(), "images": images[n_train:].copy()}
+    return train, test

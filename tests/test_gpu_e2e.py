@@ -1,0 +1,70 @@
+"""End-to-end quality parity on the GPU: the engine, driven through the reference-facing API
+(impl.util.train / embed), against metrics the UNMODIFIED reference produced on the same seeded
+two-modality problem at the same converged horizon (tests/golden/e2e_metrics.npz, written by
+oracle/make_golden_e2e.py: similarity_test and knn_test of impl/validation.py, sklearn
+trustworthiness@15).  The engine's graph is exact and its sigma solver converges, so its metrics
+may exceed the reference's; the assertions are one-sided with the reference's seed-to-seed
+spread (+ a stated slack) as tolerance."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.e2e_data import CFG, make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def similarity_metric(util, model, data, cfg):
+    """restates similarity_test, /root/reference/impl/validation.py:7-38"""
+    mats = [data[k] for k in data]
+    embeds = util.embed(model, mats, list(range(len(mats))), cfg)
+    embeds = [F.normalize(e, p=2, dim=1) for e in embeds]
+    sims = [(embeds[i] * embeds[j]).sum(dim=1) for i in range(len(mats)) for j in range(i + 1, len(mats))]
+    return torch.stack(sims, dim=1).mean(dim=1).mean().item()
+
+
+def knn_metric(util, model, data, cfg, k):
+    """restates knn_test, /root/reference/impl/validation.py:40-84 (batched instead of a row loop)"""
+    mats = [data[key] for key in data]
+    accs = []
+    for src in range(len(mats)):
+        for dst in range(src + 1, len(mats)):
+            e = util.embed(model, [mats[src], mats[dst]], [src, dst], cfg)
+            a, b = e[0].detach(), e[1].detach()
+            d = torch.cdist(a, b)
+            n = a.shape[0]
+            ar = torch.arange(n, device=a.device)[:, None]
+            fwd = (torch.topk(d, k, dim=1, largest=False).indices == ar).any(dim=1).sum().item()
+            bwd = (torch.topk(d.T, k, dim=1, largest=False).indices == ar).any(dim=1).sum().item()
+            accs.append((fwd + bwd) / (2 * n))
+    return float(np.mean(accs))
+
+
+@pytest.mark.parametrize("stream", ["device", "host"])
+def test_fit_and_transform_quality_matches_reference(golden_dir, stream, monkeypatch):
+    from sklearn.manifold import trustworthiness
+    monkeypatch.setenv("MMUMAP_SAMPLE_STREAM", stream)
+    util = importlib.import_module("impl.util")
+    ref = np.load(os.path.join(golden_dir, "e2e_metrics.npz"))
+    cfg = util.Config(**CFG)
+    train_d, test_d = make_problem()
+    torch.manual_seed(0)
+    model = util.train({k: torch.from_numpy(v) for k, v in train_d.items()}, cfg)
+    assert model.sample_stream == stream
+    td = {k: torch.from_numpy(v).cuda() for k, v in test_d.items()}
+    got = {
+        "similarity": similarity_metric(util, model, td, cfg),
+        "knn1": knn_metric(util, model, td, cfg, 1),
+        "knn5": knn_metric(util, model, td, cfg, 5),
+    }
+    for i, name in enumerate(train_d):
+        got[f"trust_{name}"] = trustworthiness(train_d[name], model.embeds[i].detach().cpu().numpy(), n_neighbors=15)
+    print({k: round(v, 4) for k, v in got.items()}, {k: np.round(ref[k], 4).tolist() for k in got})
+    slack = {"similarity": 0.05, "knn1": 0.05, "knn5": 0.05, "trust_texts": 0.02, "trust_images": 0.02}
+    for key, val in got.items():
+        lo = float(ref[key].mean()) - 3.0 * float(ref[key].std()) - slack[key]
+        assert val >= lo, f"{key}: engine {val:.4f} below reference {ref[key].mean():.4f} - tolerance ({lo:.4f})"
