@@ -49,6 +49,11 @@ WORKLOADS = {
     # BASELINE.json configs[0] (the reference's own CPU-runnable case)
     "c1": dict(desc="2000x64 Gaussian blobs, k=15, 2-D, 200 epochs", mods=[("blobs", 2000, 64, "blobs")],
                k=15, out_dim=2, epochs=200),
+    # BASELINE.json configs[2] and configs[3]: scale checks (parity-test / scaling cases, not the bench line)
+    "c3": dict(desc="1M x 768 BERT-shaped single-modality fit, k=15, 16-D", mods=[("texts", 1000000, 768, "bert")],
+               k=15, out_dim=16, epochs=600),
+    "c4": dict(desc="10M x 128 points, k=30, 2-D, 500 epochs", mods=[("blobs", 10000000, 128, "blobs")],
+               k=30, out_dim=2, epochs=500),
     # reduced C2 for functional checks of this script (NOT a benchmark configuration)
     "c2-tiny": dict(desc="C2 generators at 1/16 rows (script self-test only)",
                     mods=[("texts", 9932, 768, "bert"), ("images", 1986, 4096, "vae")], k=15, out_dim=16, epochs=50),
@@ -71,9 +76,10 @@ def make_data(workload: dict, seed: int = 0) -> dict:
         elif kind == "bert":    # BERT pooler_output: tanh-bounded
             centres = torch.randn((n_clusters, d), generator=gen)
             x = torch.tanh(centres[cluster] + torch.randn((n, d), generator=gen) * 0.5)
-        else:                   # C1: centres N(0,5^2), points = centre + N(0,1)
-            centres = torch.randn((10, d), generator=gen) * 5.0
-            x = centres[torch.arange(n) % 10] + torch.randn((n, d), generator=gen)
+        else:                   # C1/C4: centres N(0,5^2), points = centre + N(0,1)
+            nc = 10 if n <= 100000 else 1000
+            centres = torch.randn((nc, d), generator=gen) * 5.0
+            x = centres[torch.arange(n) % nc] + torch.randn((n, d), generator=gen)
         out[name] = x.contiguous()
     return out
 

@@ -196,6 +196,19 @@ int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_
                     int dim, float a, float b, uint64_t seed, const uint32_t *state, float *loss,
                     int fast_math, mmu_stream_t stream);
 
+/* K7c: invert-mode forces (inverse_transform).            ref: model.py:336-362, :437, :447
+ * head / grad_head: the Q x dim table being reconstructed in DATA space; data [n x dim]: the
+ * target modality's fitted data rows (constants); sigma / rho [n]: its fit-time sigma and rho.
+ * Gradient of mean_batches[ mean_kept dist/(w sigma_j + 1e-6)
+ *                          + mean_{kept*R} -log(1 - exp(-max(dist - rho_l, 1e-6)/(sigma_l+1e-6)) + 1e-6) ],
+ * dist = sqrt(max(|x_i - y|^2, 1e-6)), w = 1/(1 + a dist^(2b)).  Other arguments as mmu_edge_forces. */
+int mmu_invert_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
+                      const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
+                      int n_batches, int batch_size, int num_rep, int64_t rep_count, const float *head,
+                      const float *data, const float *sigma, const float *rho, float *grad_head, int dim,
+                      float a, float b, uint64_t seed, const uint32_t *state, float *loss,
+                      mmu_stream_t stream);
+
 /* K8: InfoNCE gradient for one direction (anchors e0 -> positives/negatives e1).
  * ref: model.py:364-394.  perm [num] (nullable = identity) and neg [num x n_neg] (nullable =
  * device Philox) are the host draws of model.py:373,383 in anchor order; anchors are

@@ -427,6 +427,88 @@ edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__res
     if (loss_out && lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
 }
 
+// ------------------------------------------------------------------ K7c: invert-mode forces
+// ref: model.py:336-362 (_inv_attr_loss, _inv_rep_loss) as used by _train in mode "invert"
+// (model.py:437,447).  The variable is a Q x D table in DATA space (D up to thousands), the tails
+// are rows of the fitted modality's data with their fit-time sigma / rho.  One warp per kept edge:
+// phase 1 computes the 1+R squared distances (lane-strided, coalesced), phase 2 forms
+// sum_p coef_p (x - y_p) per component and issues ONE red per component.
+constexpr int INV_MAXP = 17;      // 1 attractive + up to 16 repulsive pairs
+
+__global__ void __launch_bounds__(256)
+invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                     const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                     const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
+                     int batch_size, int num_rep, uint32_t rep_count, const float *__restrict__ head,
+                     const float *__restrict__ data, const float *__restrict__ sigma, const float *__restrict__ rho,
+                     float *__restrict__ grad_head, int dim, float a, float b, uint64_t seed,
+                     const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    const int n_kept = *kept_count;
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv_nb = 1.0f / (float)n_batches;
+    const int np = 1 + num_rep;
+    float loss_acc = 0.f;
+    for (int64_t e = wid; e < n_kept; e += n_warps) {
+        const int32_t p = kept_pos[e];
+        const int32_t i = row[p];
+        const float kb = (float)batch_kept[i / batch_size];
+        const float sc_a = inv_nb / kb, sc_r = inv_nb / (kb * (float)num_rep);
+        const float *xi = head + (int64_t)i * dim;
+        uint32_t t_idx[INV_MAXP];
+        float coef[INV_MAXP];
+        Philox4 rnd = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < INV_MAXP; ++q) {
+            t_idx[q] = 0; coef[q] = 0.f;
+            if (q >= np) continue;
+            if (q == 0) t_idx[q] = (uint32_t)col[p];
+            else if (neg) t_idx[q] = (uint32_t)neg[e * num_rep + (q - 1)];
+            else {
+                const int r = q - 1;
+                if ((r & 3) == 0) rnd = philox4x32_10((uint32_t)p, (uint32_t)(r >> 2), epoch, STREAM_NEG, k0, k1);
+                const uint32_t x = (r & 3) == 0 ? rnd.x : (r & 3) == 1 ? rnd.y : (r & 3) == 2 ? rnd.z : rnd.w;
+                t_idx[q] = urange(x, rep_count);
+            }
+            const float *yt = data + (int64_t)t_idx[q] * dim;
+            float s_raw = 0.f;
+            for (int c = lane; c < dim; c += 32) { const float df = xi[c] - yt[c]; s_raw = fmaf(df, df, s_raw); }
+            s_raw = warp_sum(s_raw);
+            const float s = fmaxf(s_raw, 1e-6f);
+            const float dist = sqrtf(s);
+            const float sg = sigma[t_idx[q]];
+            float dls, l;
+            if (q == 0) {
+                const float sb = powf(s, b);
+                const float w = 1.0f / (1.0f + a * sb);
+                const float u = w * sg + 1e-6f;
+                l = sc_a * dist / u;
+                dls = sc_a * (1.0f / (2.0f * dist * u) + dist * sg * a * b * (sb / s) * w * w / (u * u));
+            } else {
+                const float c_raw = dist - rho[t_idx[q]];
+                const float ex = expf(-fmaxf(c_raw, 1e-6f) / (sg + 1e-6f));
+                const float om = 1.0f - ex + 1e-6f;
+                l = -sc_r * logf(om);
+                dls = (c_raw >= 1e-6f) ? sc_r * (-ex / (sg + 1e-6f)) / (om * 2.0f * dist) : 0.f;
+            }
+            coef[q] = (s_raw >= 1e-6f) ? 2.0f * dls : 0.f;
+            if (lane == 0) loss_acc += l;
+        }
+        for (int c = lane; c < dim; c += 32) {
+            const float x = xi[c];
+            float g = 0.f;
+#pragma unroll
+            for (int q = 0; q < INV_MAXP; ++q)
+                if (q < np) g = fmaf(coef[q], x - data[(int64_t)t_idx[q] * dim + c], g);
+            red_add_f32(grad_head + (int64_t)i * dim + c, g);
+        }
+    }
+    if (loss_out && lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
+}
+
 // ------------------------------------------------------------------ K8: InfoNCE
 constexpr int NCE_MAX = 16;   // 1 positive + up to 15 negatives
 
@@ -728,6 +810,25 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
 #undef MMU_FORCES_DIM
 #undef MMU_FORCES_RB
 #undef MMU_FORCES
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_invert_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
+                                 const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept, int n_batches,
+                                 int batch_size, int num_rep, int64_t rep_count, const float *head, const float *data,
+                                 const float *sigma, const float *rho, float *grad_head, int dim, float a, float b,
+                                 uint64_t seed, const uint32_t *state, float *loss, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(row && col && kept_pos && kept_count && batch_kept && head && data && sigma && rho && grad_head && state,
+                  "mmu_invert_forces: null pointer");
+    MMU_CHECK_ARG(dim >= 1, "mmu_invert_forces: bad dim");
+    MMU_CHECK_ARG(num_rep >= 0 && num_rep < INV_MAXP, "mmu_invert_forces: num_rep=%d outside [0,%d)", num_rep, INV_MAXP);
+    MMU_CHECK_ARG(rep_count >= 1 && rep_count < ((int64_t)1 << 31), "mmu_invert_forces: bad rep_count");
+    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_invert_forces: bad batch geometry");
+    invert_forces_kernel<<<persistent_blocks(256, 8), 256, 0, as_stream(stream)>>>(
+        row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, num_rep, (uint32_t)rep_count, head, data,
+        sigma, rho, grad_head, dim, a, b, seed, reinterpret_cast<const OptState *>(state), loss);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

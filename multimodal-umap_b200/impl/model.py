@@ -159,9 +159,16 @@ class UMAPMixture:
                mode: str = "fit", data_indices: list | None = None, desc: str = "Training"):
         """ref: model.py:396-481."""
         native.require_cuda()
+        refs = sigmas = rhos = None
         if mode == "invert":
-            raise NotImplementedError("invert-mode optimisation: see DESIGN.md (SURVEY.md section 8 f2)")
-        refs = None
+            # ref: model.py:418-420 (tails are the target modality's data rows) and :437,:447.  The reference
+            # indexes self.encoders with the LOOP index there; the target encoder data_indices[i] is what the
+            # sigma[j_idx] / rho[j_idx] lookups need (SURVEY.md section 0 item 2) and what is used here.
+            n_modes = len(embeds) if data_indices is None else len(data_indices)
+            tgt = [data_indices[i] if data_indices is not None else i for i in range(n_modes)]
+            refs = [self.data[t] for t in tgt]
+            sigmas = [self.encoders[t].sigmas for t in tgt]
+            rhos = [self.encoders[t].rhos for t in tgt]
         if mode == "transform":
             for ref in self.embeds:                                       # model.py:399-401
                 ref.requires_grad = False
@@ -169,7 +176,7 @@ class UMAPMixture:
             refs = [self.embeds[data_indices[i]] if data_indices is not None else self.embeds[i]
                     for i in range(n_modes)]
         opt = LayoutOptimizer(embeds, [_as_graph(g) for g in graphs], self.a, self.b, num_rep, lr, alpha,
-                              batch_size, mode=mode, refs=refs,
+                              batch_size, mode=mode, refs=refs, sigmas=sigmas, rhos=rhos,
                               sample_stream=getattr(self, "sample_stream", None))
         with profiler.stage("optimise", epochs=epochs):
             out = opt.run(epochs)
@@ -201,15 +208,13 @@ class UMAPMixture:
     def inverse_transform(self, inputs: list, epochs: int, data_indices: list | None = None, num_rep: int = 8,
                           lr: float = 0.2, alpha: float = 0.5, batch_size: int = 512):
         """ref: model.py:557-585.  The reference's invert path raises a shape error as shipped
-        (SURVEY.md section 0 item 1).  Here the evident intent is implemented for the
-        initialisation -- kNN of the query embeddings among the fitted embeddings, weights
-        1/(1+a d^2b), weighted mean of the TARGET modality's data rows (Q x D) -- and returned;
-        the invert-mode refinement epochs (model.py:336-362) are the next component."""
+        (its initial value is Q x out_dim instead of Q x D).  The evident
+        intent is implemented: kNN of the query embeddings among the fitted embeddings with weights
+        1/(1+a d^2b) (model.py:206), initial value = weighted mean of the TARGET modality's data rows
+        (Q x D), then `epochs` epochs of the invert-mode losses (model.py:336-362) under Adam."""
         graphs, embeds = self.init(inputs, mode="invert", data_indices=data_indices)
-        if epochs > 0:
-            warnings.warn("inverse_transform returns the weighted-neighbour initialisation; "
-                          "invert-mode refinement epochs are not implemented yet", stacklevel=2)
-        return embeds
+        return self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="invert",
+                           data_indices=data_indices, desc=f"Inverting {len(embeds)} modalities")
 
     # ------------------------------------------------------------------ curve fit (host, one-off)
     def get_ab_coeffs(self, min_dist: float, num_iters: int = 50):

@@ -109,10 +109,14 @@ def replay_infonce_draws(num: int):
 class LayoutOptimizer:
     def __init__(self, embeds, graphs, a: float, b: float, num_rep: int, lr: float, alpha: float,
                  batch_size: int, mode: str = "fit", refs=None, sample_stream: str | None = None,
-                 seed: int | None = None, track_loss: bool = False):
+                 seed: int | None = None, track_loss: bool = False, sigmas=None, rhos=None):
         native.require_cuda()
-        if mode not in ("fit", "transform"):
+        if mode not in ("fit", "transform", "invert"):
             raise ValueError(f"Invalid mode: {mode}")
+        if mode == "invert" and (refs is None or sigmas is None or rhos is None):
+            raise ValueError("invert mode needs the target data rows and their fit-time sigma / rho")
+        self.sigmas = None if sigmas is None else [t.detach().to("cuda", torch.float32).contiguous() for t in sigmas]
+        self.rhos = None if rhos is None else [t.detach().to("cuda", torch.float32).contiguous() for t in rhos]
         self.mode = mode
         self.a, self.b = float(a), float(b)
         self.num_rep, self.lr, self.alpha = int(num_rep), float(lr), float(alpha)
@@ -144,6 +148,14 @@ class LayoutOptimizer:
 
     # ------------------------------------------------------------------ one epoch
     def _forces(self, mod: _Modality, kept_pos, kept_count, neg, batch_kept):
+        if self.mode == "invert":                                        # model.py:437,447
+            g, mi = mod.graph, self.mods.index(mod)
+            check(lib().mmu_invert_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg), ptr(batch_kept),
+                                          mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count, ptr(mod.p),
+                                          ptr(mod.ref), ptr(self.sigmas[mi]), ptr(self.rhos[mi]), ptr(mod.g), mod.dim,
+                                          self.a, self.b, self.seed, ptr(self.state), ptr(self.loss), stream()),
+                  "mmu_invert_forces")
+            return
         tail = mod.ref if self.mode == "transform" else mod.p
         grad_tail = None if self.mode == "transform" else mod.g
         g = mod.graph

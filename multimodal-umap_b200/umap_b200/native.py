@@ -57,6 +57,9 @@ _SIGNATURES = {
     "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_void_p, c_int, c_void_p]),
+    "mmu_invert_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
+                                  c_void_p, c_void_p, c_void_p]),
     "mmu_infonce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                             c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
     "mmu_infonce_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -251,6 +251,42 @@ def umap_rep_grad(y_i: np.ndarray, y_l: np.ndarray, a: float, b: float):
     return loss, coef[:, None] * diff
 
 
+def inv_attr_grad(x_i: np.ndarray, y_j: np.ndarray, sigma_j: np.ndarray, a: float, b: float):
+    """Closed form of model.py:336-348 (_inv_attr_loss) for ONE batch:
+    loss = mean_e dist / (w sigma_j + 1e-6), s = clamp(|x_i - y_j|^2, 1e-6), dist = sqrt(s),
+    w = 1/(1 + a s^b).  Returns (loss, dL/dx_i per edge); y (the data rows) are constants."""
+    diff = x_i - y_j
+    s_raw = (diff * diff).sum(axis=1)
+    s = np.maximum(s_raw, 1e-6)
+    dist = np.sqrt(s)
+    n = x_i.shape[0]
+    w = 1.0 / (1.0 + a * _pow(s, b))
+    u = w * sigma_j + 1e-6
+    loss = (dist / u).mean() if n else 0.0
+    # d/ds [dist/u] = 1/(2 dist u) - dist * (dw/ds) sigma / u^2,   dw/ds = -a b s^(b-1) w^2
+    dls = 1.0 / (2.0 * dist * u) + dist * sigma_j * a * b * _pow(s, b - 1.0) * w * w / (u * u)
+    coef = np.where(s_raw >= 1e-6, 2.0 * dls, 0.0) / max(n, 1)
+    return loss, coef[:, None] * diff
+
+
+def inv_rep_grad(x_i: np.ndarray, y_l: np.ndarray, sigma_l: np.ndarray, rho_l: np.ndarray):
+    """Closed form of model.py:350-362 (_inv_rep_loss) for ONE batch:
+    loss = mean -log(1 - exp(-clamp(dist - rho_l, 1e-6)/(sigma_l + 1e-6)) + 1e-6)."""
+    diff = x_i - y_l
+    s_raw = (diff * diff).sum(axis=1)
+    s = np.maximum(s_raw, 1e-6)
+    dist = np.sqrt(s)
+    n = x_i.shape[0]
+    c_raw = dist - rho_l
+    c = np.maximum(c_raw, 1e-6)
+    e = np.exp(-c / (sigma_l + 1e-6))
+    loss = (-np.log(1.0 - e + 1e-6)).mean() if n else 0.0
+    # dL/de = 1/(1-e+1e-6); de/dc = -e/(sigma+1e-6); dc/ddist = [c_raw >= 1e-6]; ddist/ds = 1/(2 dist)
+    dls = (1.0 / (1.0 - e + 1e-6)) * (-e / (sigma_l + 1e-6)) * (c_raw >= 1e-6) / (2.0 * dist)
+    coef = np.where(s_raw >= 1e-6, 2.0 * dls, 0.0) / max(n, 1)
+    return loss, coef[:, None] * diff
+
+
 def infonce_grad(e0: np.ndarray, e1: np.ndarray, perm: np.ndarray, negs: np.ndarray,
                  temperature: float = 0.5, chunk: int = 1000):
     """Closed form of model.py:364-394 given the replayed draws: `perm` = the randperm

@@ -68,3 +68,25 @@ def test_fit_and_transform_quality_matches_reference(golden_dir, stream, monkeyp
     for key, val in got.items():
         lo = float(ref[key].mean()) - 3.0 * float(ref[key].std()) - slack[key]
         assert val >= lo, f"{key}: engine {val:.4f} below reference {ref[key].mean():.4f} - tolerance ({lo:.4f})"
+
+
+def test_embed_and_recon_runs_and_reconstructs(monkeypatch):
+    """crossmodal path (crossmodal.py:23: embed_and_recon(model, [text], [0], [1], cfg)): the reference
+    raises here; the engine returns Q x D_image reconstructions that are
+    far closer to the true paired image rows than a random fitted image row is."""
+    monkeypatch.setenv("MMUMAP_SAMPLE_STREAM", "device")
+    util = importlib.import_module("impl.util")
+    cfg = util.Config(**dict(CFG, train_epochs=200, test_epochs=40))
+    train_d, test_d = make_problem()
+    torch.manual_seed(0)
+    model = util.train({k: torch.from_numpy(v) for k, v in train_d.items()}, cfg)
+    texts = torch.from_numpy(test_d["texts"]).cuda()
+    recon = util.embed_and_recon(model, [texts], [0], [1], cfg)
+    assert len(recon) == 1 and tuple(recon[0].shape) == (texts.shape[0], train_d["images"].shape[1])
+    r = recon[0].detach().cpu().numpy()
+    assert np.all(np.isfinite(r))
+    true = test_d["images"]
+    err = np.linalg.norm(r - true, axis=1).mean()
+    rng = np.random.default_rng(0)
+    base = np.linalg.norm(train_d["images"][rng.integers(0, 1500, true.shape[0])] - true, axis=1).mean()
+    assert err < 0.6 * base, (err, base)

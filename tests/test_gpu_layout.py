@@ -307,3 +307,58 @@ def test_edge_and_anchor_ranges_partition_the_single_gpu_stream():
     assert np.abs(a0 + b0 - f0).max() < 1e-6 * np.abs(f0).max()
     assert np.abs(a1 + b1 - f1).max() < 2e-6 * np.abs(f1).max()
     assert abs(al + bl - fl) < 1e-5 * abs(fl)
+
+
+@pytest.mark.parametrize("dim,num_rep", [(24, 4), (130, 8), (4096, 8)])
+def test_invert_forces_gradient_matches_oracle(dim, num_rep):
+    """mmu_invert_forces vs the fp64 closed form of oracle.inv_attr_grad / inv_rep_grad (pinned to the
+    reference's _inv_attr_loss/_inv_rep_loss autograd by tests/golden/invert_losses.npz), with the
+    host sample stream; includes a zero-distance pair (clamp) and a rho larger than the distance."""
+    from umap_b200.layout import LayoutOptimizer, replay_host_draws
+    rng = np.random.default_rng(dim)
+    n_ref, q, k, bs = 300, 90, 8, 32
+    data = (rng.standard_normal((n_ref, dim)) * 1.2).astype(np.float32)
+    cols = np.stack([np.sort(rng.choice(n_ref, k, replace=False)) for _ in range(q)])
+    x = (data[cols[:, 0]] + 0.3 * rng.standard_normal((q, dim))).astype(np.float32)
+    x[5] = data[cols[5, 0]]
+    sigma = (rng.random(n_ref) * 2.0 + 0.1).astype(np.float32)
+    rho = (rng.random(n_ref) * np.sqrt(dim)).astype(np.float32)
+    rho[cols[6, 1]] = 1e4
+    rows = np.repeat(np.arange(q), k)
+    vals = (0.3 + 0.7 * rng.random(q * k)).astype(np.float32)
+    graph = _coo(rows, cols.reshape(-1), vals, (q, n_ref))
+    gi = graph.indices().numpy()
+    a, b = 1.577, 0.8951
+    opt = LayoutOptimizer([torch.from_numpy(x)], [graph], a, b, num_rep, 0.01, 1.0, bs, mode="invert",
+                          refs=[torch.from_numpy(data)], sigmas=[torch.from_numpy(sigma)], rhos=[torch.from_numpy(rho)],
+                          sample_stream="host", track_loss=True)
+    mod = opt.mods[0]
+    torch.manual_seed(321)
+    kept, neg, counts = replay_host_draws(mod, num_rep)
+    nk = kept.numel()
+    mod.kept_pos[:nk].copy_(kept)
+    mod.kept_count.fill_(nk)
+    mod.batch_kept.copy_(counts)
+    neg_d = neg.cuda()
+    opt._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
+    torch.cuda.synchronize()
+    got = mod.g.cpu().numpy().astype(np.float64)
+    x64, d64, s64, r64 = x.astype(np.float64), data.astype(np.float64), sigma.astype(np.float64), rho.astype(np.float64)
+    grad = np.zeros_like(x64)
+    nb = (q + bs - 1) // bs
+    kept_np, neg_np = kept.numpy(), neg.numpy()
+    off, loss = 0, 0.0
+    for bi in range(nb):
+        c = int(counts[bi])
+        pos = kept_np[off:off + c]
+        ii, jj = gi[0][pos], gi[1][pos]
+        la, ga = orc.inv_attr_grad(x64[ii], d64[jj], s64[jj], a, b)
+        np.add.at(grad, ii, ga / nb)
+        ll = neg_np[off:off + c].reshape(-1)
+        ir = np.repeat(ii, num_rep)
+        lr_, gr = orc.inv_rep_grad(x64[ir], d64[ll], s64[ll], r64[ll])
+        np.add.at(grad, ir, gr / nb)
+        loss += (la + lr_) / nb
+        off += c
+    assert np.abs(got - grad).max() < 1e-4 * np.abs(grad).max() + 1e-9
+    assert abs(float(opt.loss.item()) - loss) < 1e-3 * abs(loss)

@@ -124,6 +124,25 @@ def test_force_terms_match_reference_autograd(golden_dir):
     assert np.allclose(grad, g["rep_grad"], rtol=1e-4, atol=1e-5)
 
 
+def test_invert_terms_match_reference_autograd(golden_dir):
+    """model.py:336-362 (_inv_attr_loss / _inv_rep_loss) incl. both clamp branches."""
+    g = _load(golden_dir, "invert_losses.npz")
+    a, b = float(g["a"]), float(g["b"])
+    x, data = g["x"].astype(np.float64), g["data"].astype(np.float64)
+    ii, jj = g["ii"], g["jj"]
+    sig, rho = g["sigma"].astype(np.float64), g["rho"].astype(np.float64)
+    la, ga = orc.inv_attr_grad(x[ii], data[jj], sig[jj], a, b)
+    grad = np.zeros_like(x)
+    np.add.at(grad, ii, ga)
+    assert abs(la - float(g["attr_loss"])) < 1e-4 * abs(float(g["attr_loss"]))
+    assert np.allclose(grad, g["attr_grad"], rtol=2e-4, atol=1e-5 * np.abs(g["attr_grad"]).max())
+    lr_, gr = orc.inv_rep_grad(x[ii], data[jj], sig[jj], rho[jj])
+    grad = np.zeros_like(x)
+    np.add.at(grad, ii, gr)
+    assert abs(lr_ - float(g["rep_loss"])) < 1e-4
+    assert np.allclose(grad, g["rep_grad"], rtol=2e-4, atol=1e-5 * np.abs(g["rep_grad"]).max())
+
+
 def test_infonce_matches_reference_autograd(golden_dir):
     g = _load(golden_dir, "losses.npz")
     e0, e1 = g["e0"], g["e1"]
