@@ -261,7 +261,7 @@ __device__ __forceinline__ float pair_coef(float s_raw, bool attractive, float a
 }
 
 template <int VEC, int LANES, int R, bool FAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
                       const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
                       const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,

@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import dist as D
-from . import native
+from . import native, profiler
 from .graph import Graph
 from .native import check, lib, ptr, stream
 
@@ -60,6 +60,7 @@ class _Modality:
             hi_row = min(self.b_hi * batch_size, self.count)
             self.e_lo, self.e_hi = (int(v) for v in graph.rowptr[[lo_row, hi_row]].tolist())
         self.kept_pos = torch.empty(max(self.e_hi - self.e_lo, 1), dtype=torch.int32, device=dev)
+        self.expected_kept = None            # sum of this rank's weights = E[kept edges per epoch] (model.py:432)
         # host copies for the replayed stream
         self._w_cpu = None
         self._rowptr_cpu = None
@@ -158,6 +159,20 @@ class LayoutOptimizer:
             return
         tail = mod.ref if self.mode == "transform" else mod.p
         grad_tail = None if self.mode == "transform" else mod.g
+        g = mod.graph
+        if profiler.enabled():
+            if mod.expected_kept is None:
+                mod.expected_kept = float(g.val[mod.e_lo:mod.e_hi].sum().item())
+            # per kept edge (2+R) row reads of d*4 B and as many row accumulations in fit mode
+            # (one, the query row, in transform mode), + 12 B of edge indices
+            rows_touched = (2 + self.num_rep) * 2 if grad_tail is not None else (2 + self.num_rep) + 1
+            nbytes = mod.expected_kept * (rows_touched * mod.dim * 4 + 12)
+            with profiler.stage("edge_forces", bytes=nbytes, edge_updates=mod.expected_kept * (1 + self.num_rep)):
+                self._launch_forces(mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail)
+            return
+        self._launch_forces(mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail)
+
+    def _launch_forces(self, mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail):
         g = mod.graph
         check(lib().mmu_edge_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg),
                                     ptr(batch_kept), mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count,
