@@ -227,6 +227,16 @@ int mmu_infonce_range(const float *e0, const float *e1, int64_t num, int64_t anc
                       uint64_t seed, uint32_t stream_id, const uint32_t *state, float *loss,
                       mmu_stream_t stream);
 
+/* Both directions of one modality pair in a single grid: forward = anchors e0 -> candidates e1 with
+ * (perm_fwd, neg_fwd, stream_id), reverse = anchors e1 -> candidates e0 with (perm_rev, neg_rev,
+ * stream_id + 1).  Equal to two mmu_infonce_range calls (the reference evaluates L_ij and L_ji on
+ * the same embeddings, model.py:467-472).  `weight` carries alpha. */
+int mmu_infonce_bidir(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                      int dim, const int32_t *perm_fwd, const int32_t *neg_fwd, const int32_t *perm_rev,
+                      const int32_t *neg_rev, int n_neg, int chunk, float weight, float temperature,
+                      float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                      const uint32_t *state, float *loss, mmu_stream_t stream);
+
 /* K9: fused Adam update over a dense table (torch.optim.Adam single-tensor semantics,
  * eps=1e-8 style denominator sqrt(v)/bc2_sqrt + eps), reading step_size / bc2_sqrt from
  * `state`; zero_grad != 0 also clears g.  Hyper-parameters are doubles because torch forms

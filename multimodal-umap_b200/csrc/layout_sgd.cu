@@ -39,42 +39,56 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
     // shard draws exactly what the single-GPU run draws for the same edges
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n4 = (nnz + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // all lanes of a warp iterate the same number of times (warp-level collectives below)
-    const int64_t first = (edge_lo >> 2) + (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
-    for (int64_t wbase = first; wbase < n4; wbase += stride) {
-        int64_t q = wbase + lane;
+    __shared__ int s_wtot[8];
+    __shared__ int s_base;
+    // every thread of a block iterates the same number of times (block-level compaction below)
+    for (int64_t bbase = (edge_lo >> 2) + (int64_t)blockIdx.x * blockDim.x; bbase < n4; bbase += stride) {
+        const int64_t q = bbase + threadIdx.x;
         int32_t pos[4];
         int cnt = 0;
         int32_t brow[4];
         if (q < n4) {
-            Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), epoch, STREAM_KEEP, k0, k1);
-            uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+            const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), epoch, STREAM_KEEP, k0, k1);
+            const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+            const int64_t e0 = q * 4;
+            float wv[4];
+            if (e0 >= edge_lo && e0 + 3 < nnz) {
+                const float4 t = *reinterpret_cast<const float4 *>(w + e0);      // quads are 16-byte aligned
+                wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wv[i] = (e0 + i >= edge_lo && e0 + i < nnz) ? w[e0 + i] : -1.0f;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                int64_t e = q * 4 + i;
-                if (e >= edge_lo && e < nnz && u01(rv[i]) < w[e]) {     // ref: model.py:432  rand < w
-                    pos[cnt] = (int32_t)e;
-                    brow[cnt] = row[e] / batch_size;
+                if (u01(rv[i]) < wv[i]) {                                         // ref: model.py:432  rand < w
+                    pos[cnt] = (int32_t)(e0 + i);
+                    brow[cnt] = row[e0 + i] / batch_size;
                     ++cnt;
                 }
             }
         }
-        // warp compaction
-        int excl = cnt;
+        // compaction: warp scan, block scan over the 8 warp totals, ONE atomic per block and iteration
+        int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, excl, o);
-            if (lane >= o) excl += t;
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        int total = __shfl_sync(0xffffffffu, excl, 31);
-        excl -= cnt;
-        int base = 0;
-        if (lane == 0 && total) base = atomicAdd(kept_count, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = 0; i < cnt; ++i) kept_pos[base + excl + i] = pos[i];
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { int t = s_wtot[u]; s_wtot[u] = tot; tot += t; }
+            s_base = tot ? atomicAdd(kept_count, tot) : 0;
+        }
+        __syncthreads();
+        const int off = s_base + s_wtot[warp] + incl - cnt;
+        for (int i = 0; i < cnt; ++i) kept_pos[off + i] = pos[i];
         // per-batch counts, aggregated on the warp's most common batch (edges are row sorted)
         unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
         int src_lane = has ? __ffs(has) - 1 : 0;
@@ -87,6 +101,7 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
         if (lane == 0 && same) atomicAdd(&batch_kept[b_ref], same);
+        __syncthreads();                                                          // s_wtot / s_base reused next iteration
     }
 }
 
@@ -513,10 +528,19 @@ invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict_
 constexpr int NCE_MAX = 16;   // 1 positive + up to 15 negatives
 
 __global__ void __launch_bounds__(128)
-infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int64_t a_lo, int64_t a_hi, int dim,
-               const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
-               float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
-               uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+infonce_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_, int64_t num, int64_t a_lo, int64_t a_hi, int dim,
+               const int32_t *__restrict__ perm_, const int32_t *__restrict__ neg_, const int32_t *__restrict__ perm_rev,
+               const int32_t *__restrict__ neg_rev, int n_neg, int chunk,
+               float weight, float temperature, float *__restrict__ grad0_, float *__restrict__ grad1_,
+               uint64_t seed, uint32_t stream_id_, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    const bool rev = blockIdx.y == 1;
+    const float *__restrict__ e0 = rev ? e1_ : e0_;
+    const float *__restrict__ e1 = rev ? e0_ : e1_;
+    float *__restrict__ grad0 = rev ? grad1_ : grad0_;
+    float *__restrict__ grad1 = rev ? grad0_ : grad1_;
+    const int32_t *__restrict__ perm = rev ? perm_rev : perm_;
+    const int32_t *__restrict__ neg = rev ? neg_rev : neg_;
+    const uint32_t stream_id = stream_id_ + (rev ? 1u : 0u);
     const int64_t t = a_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float loss_local = 0.f;
     if (t < a_hi) {
@@ -595,12 +619,23 @@ infonce_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64
 // components (dim == VEC*LANES): the anchor row and its 1+n_neg candidate rows are gathered with
 // 16-byte loads, norms and dot products are group reductions, and the gradients leave as vector
 // red.global.add -- the same closed form as infonce_kernel (ref: model.py:364-394).
-template <int VEC, int LANES>
+template <int VEC, int LANES, int MT>
 __global__ void __launch_bounds__(256)
-infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, int64_t num, int64_t a_lo, int64_t a_hi,
-                   const int32_t *__restrict__ perm, const int32_t *__restrict__ neg, int n_neg, int chunk,
-                   float weight, float temperature, float *__restrict__ grad0, float *__restrict__ grad1,
-                   uint64_t seed, uint32_t stream_id, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_, int64_t num, int64_t a_lo, int64_t a_hi,
+                   const int32_t *__restrict__ perm_, const int32_t *__restrict__ neg_, const int32_t *__restrict__ perm_rev,
+                   const int32_t *__restrict__ neg_rev, int n_neg, int chunk,
+                   float weight, float temperature, float *__restrict__ grad0_, float *__restrict__ grad1_,
+                   uint64_t seed, uint32_t stream_id_, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    // blockIdx.y == 1: the reverse direction (anchors in e1, candidates in e0) of the same pair; both
+    // read the same embedding state, so one grid evaluates L_ij + L_ji (model.py:467-472)
+    const bool rev = blockIdx.y == 1;
+    const float *__restrict__ e0 = rev ? e1_ : e0_;
+    const float *__restrict__ e1 = rev ? e0_ : e1_;
+    float *__restrict__ grad0 = rev ? grad1_ : grad0_;
+    float *__restrict__ grad1 = rev ? grad0_ : grad1_;
+    const int32_t *__restrict__ perm = rev ? perm_rev : perm_;
+    const int32_t *__restrict__ neg = rev ? neg_rev : neg_;
+    const uint32_t stream_id = stream_id_ + (rev ? 1u : 0u);
     constexpr int DIM = VEC * LANES;
     const int gl = threadIdx.x % LANES;
     const int64_t t = a_lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -611,15 +646,20 @@ infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, i
     const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
     const float wgt = weight / ((float)clen * (float)n_chunks);           // ref: model.py:392,394
     const int32_t i = perm ? perm[tt] : (int32_t)tt;
-    const int M = 1 + n_neg;
-    int32_t ids[NCE_MAX];
+    const int M = MT ? MT : 1 + n_neg;
+    constexpr int MCAP = MT ? MT : NCE_MAX;
+    int32_t ids[MCAP];
     ids[0] = i;
     if (neg) {
-        for (int m = 1; m < M; ++m) ids[m] = neg[tt * n_neg + (m - 1)];
+#pragma unroll
+        for (int m = 1; m < MCAP; ++m)
+            if (m < M) ids[m] = neg[tt * n_neg + (m - 1)];
     } else {
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
         Philox4 rnd = {0, 0, 0, 0};
-        for (int m = 1; m < M; ++m) {
+#pragma unroll
+        for (int m = 1; m < MCAP; ++m) {
+            if (m >= M) continue;
             int q = m - 1;
             if ((q & 3) == 0) rnd = philox4x32_10((uint32_t)tt, (uint32_t)(q >> 2), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
             uint32_t x = (q & 3) == 0 ? rnd.x : (q & 3) == 1 ? rnd.y : (q & 3) == 2 ? rnd.z : rnd.w;
@@ -627,15 +667,23 @@ infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, i
         }
     }
     const Vec<VEC> av = load_vec<VEC>(e0 + (int64_t)i * DIM + gl * VEC);
+    // with a compile-time candidate count all rows are gathered first (independent loads in flight)
+    Vec<VEC> evr[MT ? MT : 1];
+    if (MT) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) evr[m] = load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
+    }
     float na2 = 0.f;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) na2 = fmaf(av.v[c], av.v[c], na2);
     const float na = fmaxf(sqrtf(group_sum<LANES>(na2)), 1e-12f);       // F.normalize eps
-    float nrm[NCE_MAX], cs[NCE_MAX];
+    float nrm[MCAP], cs[MCAP];
     float mx = -__int_as_float(0x7f800000);
-    for (int m = 0; m < M; ++m) {
+#pragma unroll
+    for (int m = 0; m < MCAP; ++m) {
+        if (m >= M) continue;
         const bool ok = m == 0 || ids[m] != i;                           // ref: model.py:386
-        const Vec<VEC> ev = load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
+        const Vec<VEC> ev = MT ? evr[MT ? m : 0] : load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
         float n2 = 0.f, dt = 0.f;
 #pragma unroll
         for (int c = 0; c < VEC; ++c) { n2 = fmaf(ev.v[c], ev.v[c], n2); dt = fmaf(av.v[c], ev.v[c], dt); }
@@ -646,20 +694,23 @@ infonce_vec_kernel(const float *__restrict__ e0, const float *__restrict__ e1, i
         if (ok) mx = fmaxf(mx, cs[m] / temperature);
     }
     float den = 0.f;
-    for (int m = 0; m < M; ++m)
-        if (m == 0 || ids[m] != i) den += expf(cs[m] / temperature - mx);
+#pragma unroll
+    for (int m = 0; m < MCAP; ++m)
+        if (m < M && (m == 0 || ids[m] != i)) den += expf(cs[m] / temperature - mx);
     float loss_local = (active && gl == 0) ? wgt * -(cs[0] / temperature - mx - logf(den)) : 0.f;
     float ccs = 0.f;
     Vec<VEC> acc;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc.v[c] = 0.f;
     const float inv_na = 1.0f / na;
-    for (int m = 0; m < M; ++m) {
+#pragma unroll
+    for (int m = 0; m < MCAP; ++m) {
+        if (m >= M) continue;
         const bool ok = m == 0 || ids[m] != i;
         if (!ok) continue;                                               // group-uniform
         const float cm = expf(cs[m] / temperature - mx) / den - (m == 0 ? 1.f : 0.f);
         ccs = fmaf(cm, cs[m], ccs);
-        const Vec<VEC> ev = load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
+        const Vec<VEC> ev = MT ? evr[MT ? m : 0] : load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
         const float inv_n = 1.0f / nrm[m];
         const float sm = wgt * cm / (temperature * nrm[m]);
         Vec<VEC> g;
@@ -690,18 +741,33 @@ adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
     // torch.optim.Adam (single-tensor path) operation by operation, one rounding each: no fma
     // contraction, so that the result equals the CPU reference bit for bit.
     const float neg_step = -st->step_size, bc2_sqrt = st->bc2_sqrt;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float gg = g[i];
-        float mm = m[i];
-        float vv = v[i];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto upd = [&](float &pp, float gg, float &mm, float &vv) {
         mm = __fadd_rn(mm, __fmul_rn(omb1, __fsub_rn(gg, mm)));                        // exp_avg.lerp_(grad, 1-beta1)
         vv = __fadd_rn(__fmul_rn(vv, beta2), __fmul_rn(__fmul_rn(omb2, gg), gg));      // mul_(beta2).addcmul_(g, g, 1-beta2)
-        float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
-        p[i] = __fadd_rn(p[i], __fdiv_rn(__fmul_rn(neg_step, mm), denom));             // addcdiv_(exp_avg, denom, -step_size)
-        m[i] = mm;
-        v[i] = vv;
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+        pp = __fadd_rn(pp, __fdiv_rn(__fmul_rn(neg_step, mm), denom));                 // addcdiv_(exp_avg, denom, -step_size)
+    };
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                           reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const int64_t n4 = aligned ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4 *>(p)[i], gg = reinterpret_cast<float4 *>(g)[i];
+        float4 mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
+        upd(pp.x, gg.x, mm.x, vv.x);
+        upd(pp.y, gg.y, mm.y, vv.y);
+        upd(pp.z, gg.z, mm.z, vv.z);
+        upd(pp.w, gg.w, mm.w, vv.w);
+        reinterpret_cast<float4 *>(p)[i] = pp;
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+        if (zero_grad) reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        upd(pp, g[i], mm, vv);
+        p[i] = pp; m[i] = mm; v[i] = vv;
         if (zero_grad) g[i] = 0.f;
     }
 }
@@ -846,10 +912,34 @@ extern "C" int mmu_infonce(const float *e0, const float *e1, int64_t num, int di
                              stream_id, state, loss, stream);
 }
 
+static int infonce_launch(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                          int dim, const int32_t *perm, const int32_t *neg, const int32_t *perm_rev,
+                          const int32_t *neg_rev, int directions, int n_neg, int chunk, float weight,
+                          float temperature, float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                          const uint32_t *state, float *loss, mmu_stream_t stream);
+
 extern "C" int mmu_infonce_range(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
                                  int dim, const int32_t *perm, const int32_t *neg, int n_neg, int chunk, float weight,
                                  float temperature, float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
                                  const uint32_t *state, float *loss, mmu_stream_t stream) {
+    return infonce_launch(e0, e1, num, anchor_lo, anchor_hi, dim, perm, neg, nullptr, nullptr, 1, n_neg, chunk, weight,
+                          temperature, grad0, grad1, seed, stream_id, state, loss, stream);
+}
+
+extern "C" int mmu_infonce_bidir(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                                 int dim, const int32_t *perm_fwd, const int32_t *neg_fwd, const int32_t *perm_rev,
+                                 const int32_t *neg_rev, int n_neg, int chunk, float weight, float temperature,
+                                 float *grad0, float *grad1, uint64_t seed, uint32_t stream_id, const uint32_t *state,
+                                 float *loss, mmu_stream_t stream) {
+    return infonce_launch(e0, e1, num, anchor_lo, anchor_hi, dim, perm_fwd, neg_fwd, perm_rev, neg_rev, 2, n_neg, chunk,
+                          weight, temperature, grad0, grad1, seed, stream_id, state, loss, stream);
+}
+
+static int infonce_launch(const float *e0, const float *e1, int64_t num, int64_t anchor_lo, int64_t anchor_hi,
+                          int dim, const int32_t *perm, const int32_t *neg, const int32_t *perm_rev,
+                          const int32_t *neg_rev, int directions, int n_neg, int chunk, float weight,
+                          float temperature, float *grad0, float *grad1, uint64_t seed, uint32_t stream_id,
+                          const uint32_t *state, float *loss, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(anchor_lo >= 0 && anchor_lo <= anchor_hi && anchor_hi <= num, "mmu_infonce: bad anchor range");
     MMU_CHECK_ARG(e0 && e1 && grad0 && grad1 && state, "mmu_infonce: null pointer");
@@ -859,10 +949,15 @@ extern "C" int mmu_infonce_range(const float *e0, const float *e1, int64_t num, 
     if (anchor_hi == anchor_lo) return MMU_OK;
     const OptState *os = reinterpret_cast<const OptState *>(state);
     const int64_t cnt = anchor_hi - anchor_lo;
-#define MMU_NCE(V, L)                                                                                              \
-    infonce_vec_kernel<V, L><<<(unsigned)((cnt * L + 255) / 256), 256, 0, as_stream(stream)>>>(                   \
-        e0, e1, num, anchor_lo, anchor_hi, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed,       \
-        stream_id, os, loss)
+#define MMU_NCE_M(V, L, MTV)                                                                                       \
+    infonce_vec_kernel<V, L, MTV><<<dim3((unsigned)((cnt * L + 255) / 256), directions), 256, 0, as_stream(stream)>>>( \
+        e0, e1, num, anchor_lo, anchor_hi, perm, neg, perm_rev, neg_rev, n_neg, chunk, weight, temperature, grad0, \
+        grad1, seed, stream_id, os, loss)
+#define MMU_NCE(V, L)                                  \
+    do {                                               \
+        if (n_neg == 9) MMU_NCE_M(V, L, 10);           \
+        else MMU_NCE_M(V, L, 0);                       \
+    } while (0)
     switch (dim) {
         case 4: MMU_NCE(4, 1); break;
         case 8: MMU_NCE(4, 2); break;
@@ -871,11 +966,12 @@ extern "C" int mmu_infonce_range(const float *e0, const float *e1, int64_t num, 
         case 64: MMU_NCE(4, 16); break;
         case 128: MMU_NCE(4, 32); break;
         default:
-            infonce_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, as_stream(stream)>>>(
-                e0, e1, num, anchor_lo, anchor_hi, dim, perm, neg, n_neg, chunk, weight, temperature, grad0, grad1, seed,
-                stream_id, os, loss);
+            infonce_kernel<<<dim3((unsigned)((cnt + 127) / 128), directions), 128, 0, as_stream(stream)>>>(
+                e0, e1, num, anchor_lo, anchor_hi, dim, perm, neg, perm_rev, neg_rev, n_neg, chunk, weight, temperature,
+                grad0, grad1, seed, stream_id, os, loss);
     }
 #undef MMU_NCE
+#undef MMU_NCE_M
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
@@ -885,7 +981,7 @@ extern "C" int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, 
     using namespace mmu;
     MMU_CHECK_ARG(p && g && m && v && state, "mmu_adam_step: null pointer");
     if (n == 0) return MMU_OK;
-    int64_t want = (n + 255) / 256;
+    int64_t want = (n / 4 + 255) / 256 + 1;
     unsigned cap = persistent_blocks(256, 16);
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
     // 1-beta is formed in double and rounded once, as torch does with its Python-float betas

@@ -202,34 +202,41 @@ class LayoutOptimizer:
                 self._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
             else:
                 g = mod.graph
-                check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
-                                                  mod.n_batches, self.seed, ptr(self.state), ptr(mod.kept_pos),
-                                                  ptr(mod.kept_count), ptr(mod.batch_kept), stream()),
-                      "mmu_edge_sample_range")
+                with profiler.stage("edge_sample"):
+                    check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
+                                                      mod.n_batches, self.seed, ptr(self.state), ptr(mod.kept_pos),
+                                                      ptr(mod.kept_count), ptr(mod.batch_kept), stream()),
+                          "mmu_edge_sample_range")
                 self._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
         if self.mode == "fit":                                           # model.py:459-472
             n = len(self.mods)
             sid = 0
             for i in range(n):
                 for j in range(i + 1, n):
-                    for (s, t) in ((i, j), (j, i)):
-                        num = min(self.mods[s].count, self.mods[t].count)
-                        if num == 0:
-                            continue
-                        if host:
-                            perm, neg = replay_infonce_draws(num)
-                            perm_d = perm.pin_memory().to(dev, non_blocking=True)
-                            neg_d = neg.pin_memory().to(dev, non_blocking=True)
-                            self._infonce(self.mods[s], self.mods[t], perm_d, neg_d, sid)
-                        else:
-                            self._infonce(self.mods[s], self.mods[t], None, None, sid)
-                        sid += 1
+                    src, dst = self.mods[i], self.mods[j]
+                    num = min(src.count, dst.count)
+                    if num == 0:
+                        continue
+                    a_lo, a_hi = D.item_range(num, D.rank(), D.world())
+                    pf = nf = pr = nr = None
+                    if host:
+                        # the reference draws (randperm, randint...) for L_ij and then for L_ji (model.py:463-466)
+                        (pf, nf), (pr, nr) = replay_infonce_draws(num), replay_infonce_draws(num)
+                        pf, nf, pr, nr = (t.pin_memory().to(dev, non_blocking=True) for t in (pf, nf, pr, nr))
+                    # both directions in one grid: they read the same embedding state
+                    with profiler.stage("infonce"):
+                        check(lib().mmu_infonce_bidir(ptr(src.p), ptr(dst.p), num, a_lo, a_hi, src.dim, ptr(pf), ptr(nf),
+                                                      ptr(pr), ptr(nr), INFONCE_NEG, INFONCE_CHUNK, self.alpha, INFONCE_TAU,
+                                                      ptr(src.g), ptr(dst.g), self.seed, sid, ptr(self.state),
+                                                      ptr(self.loss), stream()), "mmu_infonce_bidir")
+                    sid += 2
         # multi-GPU: one all-reduce of the flat gradient buffer, then the identical Adam step everywhere
         D.all_reduce_sum(self.flat[1])
         check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
         p, g, m, v = self.flat
-        check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
-                                  stream()), "mmu_adam_step")
+        with profiler.stage("adam"):
+            check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
+                                      stream()), "mmu_adam_step")
         if self.loss is not None:
             D.all_reduce_sum(self.loss)
             self.losses.append(float(self.loss.item()))

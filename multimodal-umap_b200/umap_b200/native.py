@@ -64,6 +64,9 @@ _SIGNATURES = {
                             c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
     "mmu_infonce_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
                                   c_float, c_float, c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
+    "mmu_infonce_bidir": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p,
+                                  c_void_p]),
     "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p,
                               c_int, c_void_p]),
 }
