@@ -196,6 +196,24 @@ int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_
                     int dim, float a, float b, uint64_t seed, const uint32_t *state, float *loss,
                     int fast_math, mmu_stream_t stream);
 
+/* Record form of K7a/K7b (device sample stream): the sampler writes one 16-byte record
+ * {edge position, row, col, row-batch} per kept edge (kept_rec: 4 x int32 per edge, 16-byte
+ * aligned, capacity edge_hi - edge_lo) and the force kernel starts each edge from that single
+ * sequential load (prefetched one iteration ahead) instead of the kept_pos -> row/col pointer
+ * chase.  Same sampling stream and arithmetic as mmu_edge_sample_range / mmu_edge_forces with
+ * neg = NULL.  Supported for dim in {2,4,8,16,32,64,128} and num_rep in {4,8}
+ * (mmu_edge_forces_records_supported). */
+int mmu_edge_sample_records(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                            int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
+                            const uint32_t *state, int32_t *kept_rec, int32_t *kept_count,
+                            int32_t *batch_kept, mmu_stream_t stream);
+int mmu_edge_forces_records_supported(int dim, int num_rep);
+int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *kept_count, const int32_t *batch_kept,
+                            int n_batches, int num_rep, int64_t rep_count, const float *head,
+                            const float *tail, float *grad_head, float *grad_tail, int dim, float a,
+                            float b, uint64_t seed, const uint32_t *state, float *loss, int fast_math,
+                            mmu_stream_t stream);
+
 /* K7c: invert-mode forces (inverse_transform).            ref: model.py:336-362, :437, :447
  * head / grad_head: the Q x dim table being reconstructed in DATA space; data [n x dim]: the
  * target modality's fitted data rows (constants); sigma / rho [n]: its fit-time sigma and rho.

@@ -31,10 +31,12 @@ __global__ void opt_state_advance_kernel(OptState *s, double lr, double beta1, d
 
 // ------------------------------------------------------------------ K7a: edge sampling
 // thread handles 4 consecutive edges (one Philox call -> 4 uniforms)
+template <bool REC>
 __global__ void __launch_bounds__(256)
-edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w, int64_t edge_lo, int64_t nnz,
-                   int batch_size, uint64_t seed, const OptState *__restrict__ st, int32_t *__restrict__ kept_pos,
-                   int32_t *__restrict__ kept_count, int32_t *__restrict__ batch_kept) {
+edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, const float *__restrict__ w,
+                   int64_t edge_lo, int64_t nnz, int batch_size, uint64_t seed, const OptState *__restrict__ st,
+                   int32_t *__restrict__ kept_pos, int4 *__restrict__ kept_rec, int32_t *__restrict__ kept_count,
+                   int32_t *__restrict__ batch_kept) {
     // edges [edge_lo, nnz) of the global COO; the Philox counter is the GLOBAL quad index, so a
     // shard draws exactly what the single-GPU run draws for the same edges
     const uint32_t epoch = st->epoch;
@@ -49,7 +51,7 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
         const int64_t q = bbase + threadIdx.x;
         int32_t pos[4];
         int cnt = 0;
-        int32_t brow[4];
+        int32_t brow[4], erow[4];
         if (q < n4) {
             const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), epoch, STREAM_KEEP, k0, k1);
             const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
@@ -66,7 +68,8 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
             for (int i = 0; i < 4; ++i) {
                 if (u01(rv[i]) < wv[i]) {                                         // ref: model.py:432  rand < w
                     pos[cnt] = (int32_t)(e0 + i);
-                    brow[cnt] = row[e0 + i] / batch_size;
+                    erow[cnt] = row[e0 + i];
+                    brow[cnt] = erow[cnt] / batch_size;
                     ++cnt;
                 }
             }
@@ -88,7 +91,12 @@ edge_sample_kernel(const int32_t *__restrict__ row, const float *__restrict__ w,
         }
         __syncthreads();
         const int off = s_base + s_wtot[warp] + incl - cnt;
-        for (int i = 0; i < cnt; ++i) kept_pos[off + i] = pos[i];
+        for (int i = 0; i < cnt; ++i) {
+            // REC: one 16-byte record {edge position, row, col, row-batch} per kept edge, so that the force
+            // kernel starts from a single sequential load instead of a kept_pos -> row/col pointer chase
+            if (REC) kept_rec[off + i] = make_int4(pos[i], erow[i], col[pos[i]], brow[i]);
+            else kept_pos[off + i] = pos[i];
+        }
         // per-batch counts, aggregated on the warp's most common batch (edges are row sorted)
         unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
         int src_lane = has ? __ffs(has) - 1 : 0;
@@ -275,10 +283,11 @@ __device__ __forceinline__ float pair_coef(float s_raw, bool attractive, float a
     }
 }
 
-template <int VEC, int LANES, int R, bool FAST>
+template <int VEC, int LANES, int R, bool FAST, bool REC>
 __global__ void __launch_bounds__(256, 3)
 edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                      const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                      const int32_t *__restrict__ kept_pos, const int4 *__restrict__ kept_rec,
+                      const int32_t *__restrict__ kept_count,
                       const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
                       int batch_size, uint32_t rep_count, const float *__restrict__ head,
                       const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
@@ -298,6 +307,9 @@ edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict
     float loss_acc = 0.f;
     constexpr int64_t gpw = 32 / LANES;
     const int64_t wfirst = (gid / gpw) * gpw;
+    // REC: the kept-edge record of the NEXT iteration is fetched while this one is processed
+    int4 rec_next = make_int4(0, 0, 0, 0);
+    if (REC && wfirst + (gid - wfirst) < n_kept) rec_next = kept_rec[wfirst + (gid - wfirst)];
     for (int64_t e0 = wfirst; e0 < n_kept; e0 += n_groups) {
         const int64_t e = e0 + (gid - wfirst);
         const bool active = e < n_kept;
@@ -305,7 +317,18 @@ edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict
         uint32_t t_idx[NP];
         float sc_a = 0.f, sc_r = 0.f;
         t_idx[0] = 0;
-        if (active) {
+        if (REC) {
+            const int4 rec = rec_next;
+            if (e + n_groups < n_kept) rec_next = kept_rec[e + n_groups];
+            if (active) {
+                p = rec.x;
+                i = rec.y;
+                t_idx[0] = (uint32_t)rec.z;
+                const float kb = (float)batch_kept[rec.w];
+                sc_a = inv_nb / kb;
+                sc_r = inv_nb / (kb * (float)R);
+            }
+        } else if (active) {
             p = kept_pos[e];
             i = row[p];
             t_idx[0] = (uint32_t)col[p];
@@ -812,8 +835,33 @@ extern "C" int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t
     int64_t want = (n4 + 255) / 256;
     unsigned cap = persistent_blocks(256, 8);
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
-    edge_sample_kernel<<<blocks, 256, 0, st>>>(row, w, edge_lo, edge_hi, batch_size, seed,
-                                               reinterpret_cast<const OptState *>(state), kept_pos, kept_count, batch_kept);
+    edge_sample_kernel<false><<<blocks, 256, 0, st>>>(row, nullptr, w, edge_lo, edge_hi, batch_size, seed,
+                                                      reinterpret_cast<const OptState *>(state), kept_pos, nullptr,
+                                                      kept_count, batch_kept);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_edge_sample_records(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                                       int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
+                                       const uint32_t *state, int32_t *kept_rec, int32_t *kept_count,
+                                       int32_t *batch_kept, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(row && col && w && state && kept_rec && kept_count && batch_kept, "mmu_edge_sample_records: null pointer");
+    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(kept_rec) & 15) == 0, "mmu_edge_sample_records: kept_rec must be 16-byte aligned");
+    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample_records: bad batch geometry");
+    MMU_CHECK_ARG(edge_lo >= 0 && edge_hi >= edge_lo && edge_hi < ((int64_t)1 << 31), "mmu_edge_sample_records: bad edge range");
+    cudaStream_t st = as_stream(stream);
+    MMU_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st));
+    MMU_CUDA(cudaMemsetAsync(batch_kept, 0, sizeof(int32_t) * (size_t)n_batches, st));
+    if (edge_hi == edge_lo) return MMU_OK;
+    int64_t n4 = (edge_hi + 3) / 4 - edge_lo / 4;
+    int64_t want = (n4 + 255) / 256;
+    unsigned cap = persistent_blocks(256, 8);
+    unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
+    edge_sample_kernel<true><<<blocks, 256, 0, st>>>(row, col, w, edge_lo, edge_hi, batch_size, seed,
+                                                     reinterpret_cast<const OptState *>(state), nullptr,
+                                                     reinterpret_cast<int4 *>(kept_rec), kept_count, batch_kept);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
@@ -846,13 +894,13 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
 #define MMU_FORCES_RB(V, L, RR)                                                                                  \
     do {                                                                                                         \
         if (fast_math)                                                                                           \
-            edge_forces_rb_kernel<V, L, RR, true><<<blocks, 256, 0, st>>>(                                       \
-                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, (uint32_t)rep_count,     \
-                head, tail, grad_head, grad_tail, a, b, seed, os, loss);                                         \
+            edge_forces_rb_kernel<V, L, RR, true, false><<<blocks, 256, 0, st>>>(                                \
+                row, col, kept_pos, nullptr, kept_count, neg, batch_kept, n_batches, batch_size,                 \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
         else                                                                                                     \
-            edge_forces_rb_kernel<V, L, RR, false><<<blocks, 256, 0, st>>>(                                      \
-                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, (uint32_t)rep_count,     \
-                head, tail, grad_head, grad_tail, a, b, seed, os, loss);                                         \
+            edge_forces_rb_kernel<V, L, RR, false, false><<<blocks, 256, 0, st>>>(                               \
+                row, col, kept_pos, nullptr, kept_count, neg, batch_kept, n_batches, batch_size,                 \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
     } while (0)
 #define MMU_FORCES_DIM(V, L)                                      \
     do {                                                          \
@@ -876,6 +924,57 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
 #undef MMU_FORCES_DIM
 #undef MMU_FORCES_RB
 #undef MMU_FORCES
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_edge_forces_records_supported(int dim, int num_rep) {
+    const bool d = dim == 2 || dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128;
+    return (d && (num_rep == 8 || num_rep == 4)) ? 1 : 0;
+}
+
+extern "C" int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *kept_count, const int32_t *batch_kept,
+                                       int n_batches, int num_rep, int64_t rep_count, const float *head,
+                                       const float *tail, float *grad_head, float *grad_tail, int dim, float a, float b,
+                                       uint64_t seed, const uint32_t *state, float *loss, int fast_math,
+                                       mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(kept_rec && kept_count && batch_kept && head && tail && grad_head && state,
+                  "mmu_edge_forces_records: null pointer");
+    MMU_CHECK_ARG(mmu_edge_forces_records_supported(dim, num_rep), "mmu_edge_forces_records: unsupported dim=%d / num_rep=%d",
+                  dim, num_rep);
+    MMU_CHECK_ARG(rep_count >= 1 && rep_count < ((int64_t)1 << 31) && n_batches >= 1, "mmu_edge_forces_records: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    const OptState *os = reinterpret_cast<const OptState *>(state);
+    const int4 *rec = reinterpret_cast<const int4 *>(kept_rec);
+    unsigned blocks = persistent_blocks(256, 8);
+#define MMU_FREC(V, L, RR)                                                                                       \
+    do {                                                                                                         \
+        if (fast_math)                                                                                           \
+            edge_forces_rb_kernel<V, L, RR, true, true><<<blocks, 256, 0, st>>>(                                 \
+                nullptr, nullptr, nullptr, rec, kept_count, nullptr, batch_kept, n_batches, 1,                   \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
+        else                                                                                                     \
+            edge_forces_rb_kernel<V, L, RR, false, true><<<blocks, 256, 0, st>>>(                                \
+                nullptr, nullptr, nullptr, rec, kept_count, nullptr, batch_kept, n_batches, 1,                   \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
+    } while (0)
+#define MMU_FREC_DIM(V, L)                       \
+    do {                                         \
+        if (num_rep == 8) MMU_FREC(V, L, 8);     \
+        else MMU_FREC(V, L, 4);                  \
+    } while (0)
+    switch (dim) {
+        case 2: MMU_FREC_DIM(2, 1); break;
+        case 4: MMU_FREC_DIM(4, 1); break;
+        case 8: MMU_FREC_DIM(4, 2); break;
+        case 16: MMU_FREC_DIM(4, 4); break;
+        case 32: MMU_FREC_DIM(4, 8); break;
+        case 64: MMU_FREC_DIM(4, 16); break;
+        default: MMU_FREC_DIM(4, 32); break;
+    }
+#undef MMU_FREC_DIM
+#undef MMU_FREC
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

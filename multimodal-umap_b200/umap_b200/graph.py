@@ -123,9 +123,40 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         # multi-GPU fit: query row-blocks per rank, all-gather of the per-row results
         lo, hi = D.row_block(db.shape[0], D.rank(), D.world())
         with profiler.stage("knn", flops=2.0 * (hi - lo) * db.shape[0] * db.shape[1], kernel=kernel):
+            if os.environ.get("MMUMAP_KNN_DIST", "rows") == "ring":
+                # row-sharded DATABASE: each rank only touches its own rows of `db`; the shards rotate round
+                # the ranks peer-to-peer (NCCL send/recv over NVLink) under a running per-row top-k merge
+                return knn_ring(_f32c(db)[lo:hi].contiguous(), db.shape[0], k, exclude_self, search)
             return D.knn_sharded_rows(_f32c(db), k, exclude_self, search)
     with profiler.stage("knn", flops=2.0 * query.shape[0] * db.shape[0] * db.shape[1], kernel=kernel):
         return search(query, db, k, exclude_self, 0)
+
+
+def knn_merge(idx_a: torch.Tensor, dist_a: torch.Tensor, idx_b: torch.Tensor, dist_b: torch.Tensor):
+    """K3: merge two sorted per-row lists into one sorted top-k (mmu_knn_merge)."""
+    oi, od = torch.empty_like(idx_a), torch.empty_like(dist_a)
+    check(lib().mmu_knn_merge(ptr(idx_a.contiguous()), ptr(dist_a.contiguous()), ptr(idx_b.contiguous()),
+                              ptr(dist_b.contiguous()), idx_a.shape[0], idx_a.shape[1], ptr(oi), ptr(od), stream()),
+          "mmu_knn_merge")
+    return oi, od
+
+
+def knn_ring(x_local: torch.Tensor, n_total: int, k: int, exclude_self: bool, search):
+    """Row-sharded database kNN (dist.ring_knn) followed by the all-gather of the row blocks."""
+    import torch.distributed as tdist
+    li, ld = D.ring_knn(x_local, n_total, k, exclude_self, search, knn_merge)
+    w = D.world()
+    per = D.block_size(n_total, w)
+    ip = torch.full((per, k), -1, dtype=torch.int32, device=x_local.device)
+    dp = torch.full((per, k), float("inf"), dtype=torch.float32, device=x_local.device)
+    if li is not None:
+        ip[: li.shape[0]] = li
+        dp[: ld.shape[0]] = ld
+    ia = torch.empty((w * per, k), dtype=torch.int32, device=x_local.device)
+    da = torch.empty((w * per, k), dtype=torch.float32, device=x_local.device)
+    tdist.all_gather_into_tensor(ia, ip)
+    tdist.all_gather_into_tensor(da, dp)
+    return ia[:n_total].contiguous(), da[:n_total].contiguous()
 
 
 def smooth_knn(idx: torch.Tensor, dist: torch.Tensor, solver: str = "bisect", n_iter: int | None = None):

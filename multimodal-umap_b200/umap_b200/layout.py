@@ -61,6 +61,7 @@ class _Modality:
             self.e_lo, self.e_hi = (int(v) for v in graph.rowptr[[lo_row, hi_row]].tolist())
         self.kept_pos = torch.empty(max(self.e_hi - self.e_lo, 1), dtype=torch.int32, device=dev)
         self.expected_kept = None            # sum of this rank's weights = E[kept edges per epoch] (model.py:432)
+        self.kept_rec = None                 # [n_edges, 4] int32 kept-edge records (device stream, record kernels)
         # host copies for the replayed stream
         self._w_cpu = None
         self._rowptr_cpu = None
@@ -143,6 +144,11 @@ class LayoutOptimizer:
         self.seed = D.same_on_all_ranks(int(seed))
         # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
         self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
+        # record-form kernels: measured equal to the position form on B200 (the force kernel is bound by
+        # L2 random-access throughput, not by the kept_pos -> row/col chain), so they stay opt-in
+        self.use_records = (self.sample_stream == "device" and mode in ("fit", "transform")
+                            and os.environ.get("MMUMAP_RECORDS", "0") == "1"
+                            and all(lib().mmu_edge_forces_records_supported(m.dim, self.num_rep) for m in self.mods))
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
         self.losses: list[float] = []
         self.edge_updates = 0          # host-stream mode counts them exactly; device mode reads kept_count
@@ -174,6 +180,13 @@ class LayoutOptimizer:
 
     def _launch_forces(self, mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail):
         g = mod.graph
+        if kept_pos is None:                                             # record form (device stream)
+            check(lib().mmu_edge_forces_records(ptr(mod.kept_rec), ptr(kept_count), ptr(batch_kept), mod.n_batches,
+                                                self.num_rep, mod.rep_count, ptr(mod.p), ptr(tail), ptr(mod.g),
+                                                ptr(grad_tail), mod.dim, self.a, self.b, self.seed, ptr(self.state),
+                                                ptr(self.loss), int(self.fast_math), stream()),
+                  "mmu_edge_forces_records")
+            return
         check(lib().mmu_edge_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg),
                                     ptr(batch_kept), mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count,
                                     ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a, self.b,
@@ -200,6 +213,16 @@ class LayoutOptimizer:
                 mod.batch_kept.copy_(counts.pin_memory(), non_blocking=True)
                 neg_d = neg.pin_memory().to(dev, non_blocking=True) if n else torch.zeros(1, dtype=torch.int32, device=dev)
                 self._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
+            elif self.use_records:
+                g = mod.graph
+                if mod.kept_rec is None:
+                    mod.kept_rec = torch.empty((max(mod.e_hi - mod.e_lo, 1), 4), dtype=torch.int32, device=dev)
+                with profiler.stage("edge_sample"):
+                    check(lib().mmu_edge_sample_records(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi,
+                                                        mod.batch_size, mod.n_batches, self.seed, ptr(self.state),
+                                                        ptr(mod.kept_rec), ptr(mod.kept_count), ptr(mod.batch_kept),
+                                                        stream()), "mmu_edge_sample_records")
+                self._forces(mod, None, mod.kept_count, None, mod.batch_kept)
             else:
                 g = mod.graph
                 with profiler.stage("edge_sample"):

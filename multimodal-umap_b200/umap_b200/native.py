@@ -57,6 +57,11 @@ _SIGNATURES = {
     "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_void_p, c_int, c_void_p]),
+    "mmu_edge_sample_records": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_forces_records_supported": (c_int, [c_int, c_int]),
+    "mmu_edge_forces_records": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int, c_float, c_float, c_uint64, c_void_p, c_void_p, c_int, c_void_p]),
     "mmu_invert_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
                                   c_void_p, c_void_p, c_void_p]),

@@ -1,0 +1,55 @@
+"""Multi-GPU parity check (launch with torch.distributed.run, one rank per GPU):
+row-block kNN and database-ring kNN vs the single-GPU search, and the edge-sharded optimiser vs the
+single-GPU optimiser from the same state (same seeds: identical sample stream, so the embeddings
+may differ only by the order of fp32 atomics / the all-reduce)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "multimodal-umap_b200")]
+import numpy as np
+import torch
+import torch.distributed as dist
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from umap_b200 import dist as D, graph as G, knn_tc
+from umap_b200.layout import LayoutOptimizer
+
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator(device="cuda").manual_seed(0)
+n, d, k = 50000, 256, 15
+x = (3.0 * torch.randn((64, d), generator=g, device="cuda")[torch.arange(n, device="cuda") % 64]
+     + torch.randn((n, d), generator=g, device="cuda")).contiguous()
+ref_i, ref_d = knn_tc.knn_tc(x, x, k, True)
+for mode in ("rows", "ring"):
+    os.environ["MMUMAP_KNN_DIST"] = mode
+    i, dd = G.knn_graph(x, x, k, True)
+    ok = bool(torch.equal(i, ref_i)) and bool(torch.equal(dd.view(torch.int32), ref_d.view(torch.int32)))
+    print(f"[rank {rank}] kNN dist mode {mode}: bit-exact vs single GPU = {ok}", flush=True)
+    assert ok
+col, w, _, _ = G.smooth_knn(ref_i, ref_d)
+sym = G.fuzzy_union(col, w)
+y0 = torch.randn((n, 16), generator=g, device="cuda") * 0.01
+y1 = torch.randn((n // 2, 16), generator=g, device="cuda") * 0.01
+sym2 = G.fuzzy_union(col[: n // 2].clamp(max=n // 2 - 1).sort(dim=1).values, w[: n // 2])
+def run(sharded):
+    if not sharded:
+        saved = (D.world, D.rank)
+        D.world, D.rank = (lambda: 1), (lambda: 0)
+    try:
+        opt = LayoutOptimizer([y0, y1], [sym, sym2], 1.577, 0.8951, 8, 0.01, 1.0, 256, mode="fit", sample_stream="device", seed=3)
+        out = opt.run(5)
+        kept = opt.kept_last_epoch()
+    finally:
+        if not sharded:
+            D.world, D.rank = saved
+    return out, kept
+(a0, a1), ka = run(True)
+(b0, b1), kb = run(False)
+err = max(float((a0 - b0).abs().max()), float((a1 - b1).abs().max()))
+print(f"[rank {rank}] optimiser 5 epochs: sharded({world}) vs single max|diff| = {err:.3e}; kept {ka} vs {kb}", flush=True)
+assert ka == kb and err < 5e-5
+dist.barrier()
+if rank == 0:
+    print("multi-GPU parity OK", flush=True)
+dist.destroy_process_group()

@@ -362,3 +362,48 @@ def test_invert_forces_gradient_matches_oracle(dim, num_rep):
         off += c
     assert np.abs(got - grad).max() < 1e-4 * np.abs(grad).max() + 1e-9
     assert abs(float(opt.loss.item()) - loss) < 1e-3 * abs(loss)
+
+
+@pytest.mark.parametrize("mode", ["fit", "transform"])
+@pytest.mark.parametrize("dim,num_rep", [(2, 8), (16, 8), (16, 4), (128, 8)])
+def test_record_kernels_equal_position_kernels(dim, num_rep, mode, monkeypatch):
+    """Device sample stream: the record-form sampler + force kernel (one 16-byte record per kept edge,
+    prefetched) draw the same edges and negatives and produce the same gradient as the
+    position-form kernels (differences only from the order of the floating-point atomics)."""
+    from umap_b200.layout import LayoutOptimizer
+    rng = np.random.default_rng(dim + num_rep)
+    n, k, bs = 3000, 12, 256
+    y = (rng.standard_normal((n, dim)) * 0.3).astype(np.float32)
+    ref = (rng.standard_normal((n + 100, dim)) * 0.3).astype(np.float32)
+    cols = np.stack([np.sort(rng.choice(n, k, replace=False)) for _ in range(n)])
+    graph = _coo(np.repeat(np.arange(n), k), cols.reshape(-1), rng.random(n * k).astype(np.float32), (n, n + (100 if mode == "transform" else 0)))
+    grads = []
+    for rec in ("1", "0"):
+        monkeypatch.setenv("MMUMAP_RECORDS", rec)
+        opt = LayoutOptimizer([torch.from_numpy(y)], [graph], 1.577, 0.8951, num_rep, 0.01, 1.0, bs, mode=mode,
+                              refs=[torch.from_numpy(ref)] if mode == "transform" else None, sample_stream="device", seed=5)
+        assert opt.use_records == (rec == "1")
+        mod = opt.mods[0]
+        g = mod.graph
+        if opt.use_records:
+            mod.kept_rec = torch.empty((g.nnz, 4), dtype=torch.int32, device="cuda")
+            from umap_b200.native import check, lib, ptr, stream
+            check(lib().mmu_edge_sample_records(ptr(g.row), ptr(g.col), ptr(g.val), 0, g.nnz, bs, mod.n_batches, opt.seed,
+                                                ptr(opt.state), ptr(mod.kept_rec), ptr(mod.kept_count), ptr(mod.batch_kept),
+                                                stream()), "records")
+            opt._forces(mod, None, mod.kept_count, None, mod.batch_kept)
+            nk = int(mod.kept_count.item())
+            recs = mod.kept_rec[:nk].cpu().numpy()
+            assert np.array_equal(recs[:, 1], g.row.cpu().numpy()[recs[:, 0]])
+            assert np.array_equal(recs[:, 2], g.col.cpu().numpy()[recs[:, 0]])
+            assert np.array_equal(recs[:, 3], recs[:, 1] // bs)
+            kept_a = np.sort(recs[:, 0])
+        else:
+            from umap_b200.native import check, lib, ptr, stream
+            check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), 0, g.nnz, bs, mod.n_batches, opt.seed, ptr(opt.state),
+                                              ptr(mod.kept_pos), ptr(mod.kept_count), ptr(mod.batch_kept), stream()), "pos")
+            opt._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
+            nk = int(mod.kept_count.item())
+            assert np.array_equal(np.sort(mod.kept_pos[:nk].cpu().numpy()), kept_a)
+        grads.append(mod.g.cpu().numpy().astype(np.float64))
+    assert np.abs(grads[0] - grads[1]).max() < 2e-5 * np.abs(grads[1]).max()
