@@ -117,7 +117,8 @@ int mmu_invert_weights(const int32_t *idx, const float *dist, int64_t n_rows, in
 
 /* ------------------------------------------------------------------------------------
  * K5  fuzzy union S = G + G^T - G*G^T     ref: model.py:271
- * G is the fixed-degree graph from K4 (n x k, columns ascending per row).  G^T is built by
+ * G is the fixed-degree graph from K4 (n x k, columns ascending AND DISTINCT per row, as a kNN
+ * result is; rows with repeated columns are outside the contract).  G^T is built by
  * a stable LSD radix sort on the column key; each row then merges its two sorted lists.
  * Output is coalesced COO/CSR: out_rowptr [n+1], out_row/out_col/out_val with capacity
  * 2*n*k entries, sorted by (row, col); values fl(fl(a+b)-fl(a*b)) on mutual edges.

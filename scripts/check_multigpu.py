@@ -31,7 +31,10 @@ col, w, _, _ = G.smooth_knn(ref_i, ref_d)
 sym = G.fuzzy_union(col, w)
 y0 = torch.randn((n, 16), generator=g, device="cuda") * 0.01
 y1 = torch.randn((n // 2, 16), generator=g, device="cuda") * 0.01
-sym2 = G.fuzzy_union(col[: n // 2].clamp(max=n // 2 - 1).sort(dim=1).values, w[: n // 2])
+xh = x[: n // 2].contiguous()
+i2, d2 = knn_tc.knn_tc(xh, xh, k, True)
+col2, w2, _, _ = G.smooth_knn(i2, d2)
+sym2 = G.fuzzy_union(col2, w2)
 def run(sharded):
     if not sharded:
         saved = (D.world, D.rank)
@@ -46,9 +49,15 @@ def run(sharded):
     return out, kept
 (a0, a1), ka = run(True)
 (b0, b1), kb = run(False)
+(c0, c1), kc = run(False)
 err = max(float((a0 - b0).abs().max()), float((a1 - b1).abs().max()))
-print(f"[rank {rank}] optimiser 5 epochs: sharded({world}) vs single max|diff| = {err:.3e}; kept {ka} vs {kb}", flush=True)
-assert ka == kb and err < 5e-5
+rerun = max(float((c0 - b0).abs().max()), float((c1 - b1).abs().max()))
+mean_err = float((a0 - b0).abs().mean())
+print(f"[rank {rank}] optimiser 5 epochs: sharded({world}) vs single max|diff| = {err:.3e} (mean {mean_err:.2e}); "
+      f"single vs its own rerun (atomic order) = {rerun:.3e}; kept {ka} vs {kb}", flush=True)
+# Adam turns near-zero gradient entries into +-lr steps, so the order of the fp32 atomics alone moves a few
+# coordinates by O(lr) between two identical single-GPU runs; the sharded run must stay in that band
+assert ka == kb == kc and err < max(10 * rerun, 2e-3) and mean_err < 1e-5
 dist.barrier()
 if rank == 0:
     print("multi-GPU parity OK", flush=True)
