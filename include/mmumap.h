@@ -84,13 +84,22 @@ int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_
  *   stats[0] rows left for the exhaustive kernel, stats[1] candidates rescored, stats[2] rows
  *   certified, stats[3] reserved (4 x int32, zeroed by the call); fallback_rows: [n_query].
  * query_is_db != 0 (fit mode): query and db are the same array and share one fp16 copy.
- * out_idx holds db row numbers; exclude_self drops the pair j == query_index_base + q. */
+ * out_idx holds db row numbers; exclude_self drops the pair j == query_index_base + q, or
+ * j == query_gid[q] when query_gid (nullable, [n_query]) is given (gathered query rows).
+ * min_splits (0..8, 0 = automatic): the database range is searched in at least that many splits,
+ * each keeping its own 64 candidates per row -- a deeper candidate pool for rows whose
+ * neighbourhood gaps are too small for one list to be certified (the host retries the rows of
+ * fallback_rows with min_splits = 8 and precision = 1 before resorting to the exhaustive kernel).
+ * precision 0: fp16 operands (error bound ~2^-9 |x||y| on a score).  precision 1: error-compensated
+ * split operands hi + lo (three times the MMA work, error bound ~2^-20 |x||y|) for data whose
+ * neighbour gaps are small against |x||y| (low dimension, norms large against local distances). */
 #define MMU_KNN_TC_MAX_K 32
-size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db);
+size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits,
+                                  int precision);
 int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
-               int exclude_self, int64_t query_index_base, int query_is_db, void *workspace,
-               size_t workspace_bytes, int32_t *out_idx, float *out_dist, int32_t *stats,
-               int32_t *fallback_rows, mmu_stream_t stream);
+               int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
+               int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
+               float *out_dist, int32_t *stats, int32_t *fallback_rows, mmu_stream_t stream);
 
 /* K3: merge two sorted per-row lists (e.g. from two db shards) into one sorted top-k. */
 int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_b,

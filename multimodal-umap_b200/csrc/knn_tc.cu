@@ -176,15 +176,21 @@ __global__ void tc_finish_stats_kernel(const float *__restrict__ partial, int n_
 
 // one warp per row: fp16 copy of (x - mean) * scale, zero padded to dim_pad; squared norm of the
 // unrounded values; rows >= n are zero with norm = pad_norm
+// split == 0: one fp16 value per component.  split == 1 / 2: error-compensated operands for the
+// second certification level -- every value v is written as hi = fp16(v) and lo = fp16(v - hi), the row
+// is three dim_pad-wide sections [hi | hi | lo] (split 1, query side) or [hi | lo | hi] (split 2, database
+// side), so that the unchanged contraction kernel evaluates hi.hi + hi.lo + lo.hi (error ~2^-21 |x||y|
+// instead of 2^-10 |x||y|) with a three times longer k loop.
 __global__ void __launch_bounds__(256)
-tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim, int dim_pad,
+tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim, int dim_pad, int split,
                   const float *__restrict__ mean, const uint32_t *__restrict__ prm, __half *__restrict__ x16,
                   float *__restrict__ norm2, float pad_norm, uint32_t *__restrict__ max_norm_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n_pad) return;
     const float scale = __uint_as_float(prm[0]);
-    __half *dst = x16 + row * dim_pad;
+    const int width = split ? 3 * dim_pad : dim_pad;
+    __half *dst = x16 + row * width;
     float acc = 0.f;
     if (row < n) {
         const float *src = x + row * dim;
@@ -193,7 +199,14 @@ tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim
             float v1 = (c + 1 < dim) ? (src[c + 1] - mean[c + 1]) * scale : 0.f;
             acc = fmaf(v0, v0, acc);
             acc = fmaf(v1, v1, acc);
-            *reinterpret_cast<__half2 *>(dst + c) = __floats2half2_rn(v0, v1);
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            *reinterpret_cast<__half2 *>(dst + c) = hi;
+            if (split) {
+                const float2 hf = __half22float2(hi);
+                const __half2 lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                *reinterpret_cast<__half2 *>(dst + dim_pad + c) = split == 1 ? hi : lo;
+                *reinterpret_cast<__half2 *>(dst + 2 * dim_pad + c) = split == 1 ? lo : hi;
+            }
         }
         acc = warp_sum(acc);
         if (lane == 0) {
@@ -201,7 +214,7 @@ tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim
             if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(acc));
         }
     } else {
-        for (int c = lane * 2; c < dim_pad; c += 64) *reinterpret_cast<__half2 *>(dst + c) = __floats2half2_rn(0.f, 0.f);
+        for (int c = lane * 2; c < width; c += 64) *reinterpret_cast<__half2 *>(dst + c) = __floats2half2_rn(0.f, 0.f);
         if (lane == 0) norm2[row] = pad_norm;
     }
 }
@@ -411,6 +424,7 @@ struct RsParams {
     int64_t n_query, n_db;
     int dim, k, exclude_self;
     int64_t query_index_base;
+    const int32_t *query_gid;   // nullable: db index of query row q (self exclusion for gathered query rows)
     const float *xnorm;      // [n_query_pad] |X_q|^2 (centred, scaled)
     const uint32_t *prm;     // prm[1] = largest |Y|^2 bits
     int n_splits;
@@ -419,6 +433,7 @@ struct RsParams {
     const float *tau;
     float c_rel;             // error bound of -2 X.Y relative to |X||Y|
     float c_norm;            // relative error bound of the fp32 norm |Y|^2
+    float c_abs;             // absolute error (scaled units) from fp16 underflow of tiny components
     float gamma;             // relative error bound of the canonical fp32 squared distance
     int32_t *out_idx;
     float *out_dist;
@@ -451,7 +466,7 @@ knn_tc_rescore_kernel(const RsParams p) {
     if (q >= p.n_query) return;
     const int qblock = (int)(q / TC_BM), r = (int)(q % TC_BM);
     const int n_cand = p.n_splits * TC_KP;                     // <= 512
-    const int64_t qglob = q + p.query_index_base;
+    const int64_t qglob = p.query_gid ? (int64_t)p.query_gid[q] : q + p.query_index_base;
     const int64_t base = (int64_t)qblock * p.n_splits * TC_KP * TC_BM;
 
     // gather this row's candidates: entry e = split * KP + slot
@@ -507,7 +522,7 @@ knn_tc_rescore_kernel(const RsParams p) {
     const float x2 = p.xnorm[q];
     const float ymax2 = __uint_as_float(p.prm[1]);
     // |S~ - S| <= eps for every db point; the few ulps of the epilogue's own fp32 ops are in c_rel
-    const float eps = p.c_rel * sqrtf(x2) * sqrtf(ymax2) + p.c_norm * ymax2;
+    const float eps = p.c_rel * sqrtf(x2) * sqrtf(ymax2) + p.c_norm * ymax2 + p.c_abs;
     const float upper = kth + eps;                              // >= true k-th smallest score
     const float margin = 2.2f * p.gamma * fmaxf(upper + x2, 0.f) + 1e-30f;
     const float cut = upper + margin;                           // true score above this: cannot be in the top k
@@ -669,15 +684,17 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct TcLayout {
     int64_t q_pad, n_pad;
-    int dim_pad, n_qblocks, n_tiles, n_splits, tiles_per_split, stat_blocks, rows_per_stat_block;
+    int dim_pad, width, n_qblocks, n_tiles, n_splits, tiles_per_split, stat_blocks, rows_per_stat_block;
     bool shared_operand;
     size_t off_prm, off_mean, off_partial, off_db16, off_ynorm, off_q16, off_xnorm, off_cidx, off_cscore, off_tau, total;
 };
 
-static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_operand) {
+static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_operand, int min_splits, int split) {
     TcLayout L;
+    if (split) shared_operand = false;               // the two operands differ: [hi|hi|lo] vs [hi|lo|hi]
     L.shared_operand = shared_operand;
     L.dim_pad = (int)round_up(dim, TC_BK);
+    L.width = split ? 3 * L.dim_pad : L.dim_pad;
     L.n_pad = round_up(n_db, TC_BN);                 // also a multiple of TC_BM
     L.q_pad = shared_operand ? L.n_pad : round_up(n_query, TC_BM);
     L.n_qblocks = (int)(round_up(n_query, TC_BM) / TC_BM);
@@ -693,6 +710,11 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
         double eff = waves / (double)((int64_t)waves + (waves > (int64_t)waves ? 1 : 0));
         if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
     }
+    // more splits = deeper candidate pool (64 per split): the caller raises min_splits for rows whose
+    // neighbourhood gaps are too small for one list to certify
+    if (min_splits > best_s) best_s = min_splits;
+    if (best_s > 8) best_s = 8;
+    if (best_s > L.n_tiles) best_s = L.n_tiles;
     L.n_splits = best_s;
     L.tiles_per_split = (L.n_tiles + L.n_splits - 1) / L.n_splits;
     L.stat_blocks = (int)((n_db + 31) / 32 < 296 ? (n_db + 31) / 32 : 296);
@@ -702,9 +724,9 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     L.off_prm = o; o += 256;
     L.off_mean = o; o += align256(sizeof(float) * L.dim_pad);
     L.off_partial = o; o += align256(sizeof(float) * (size_t)296 * dim) * (shared_operand ? 1 : 2);
-    L.off_db16 = o; o += align256(sizeof(__half) * (size_t)L.n_pad * L.dim_pad);
+    L.off_db16 = o; o += align256(sizeof(__half) * (size_t)L.n_pad * L.width);
     L.off_ynorm = o; o += align256(sizeof(float) * (size_t)L.n_pad);
-    L.off_q16 = o; if (!shared_operand) o += align256(sizeof(__half) * (size_t)L.q_pad * L.dim_pad);
+    L.off_q16 = o; if (!shared_operand) o += align256(sizeof(__half) * (size_t)L.q_pad * L.width);
     L.off_xnorm = o; o += align256(sizeof(float) * (size_t)L.q_pad);
     size_t cand = (size_t)L.n_qblocks * L.n_splits * TC_KP * TC_BM;
     L.off_cidx = o; o += align256(sizeof(int32_t) * cand);
@@ -716,15 +738,16 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
 
 }  // namespace mmu
 
-extern "C" size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db) {
+extern "C" size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits,
+                                             int precision) {
     if (n_query <= 0 || n_db <= 0 || dim <= 0) return 0;
-    return mmu::tc_layout(n_query, n_db, dim, query_is_db != 0).total;
+    return mmu::tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0).total;
 }
 
 extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
-                          int exclude_self, int64_t query_index_base, int query_is_db, void *workspace,
-                          size_t workspace_bytes, int32_t *out_idx, float *out_dist, int32_t *stats,
-                          int32_t *fallback_rows, mmu_stream_t stream) {
+                          int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
+                          int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
+                          float *out_dist, int32_t *stats, int32_t *fallback_rows, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(query && db && workspace && out_idx && out_dist && stats && fallback_rows, "mmu_knn_tc: null pointer");
     MMU_CHECK_ARG(k >= 1 && k <= MMU_KNN_TC_MAX_K, "mmu_knn_tc: k=%d outside [1,%d]", k, MMU_KNN_TC_MAX_K);
@@ -735,7 +758,10 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     cudaStream_t st = as_stream(stream);
     MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
     if (n_query == 0) return MMU_OK;
-    const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0);
+    MMU_CHECK_ARG(min_splits >= 0 && min_splits <= 8, "mmu_knn_tc: min_splits outside [0,8]");
+    MMU_CHECK_ARG(precision == 0 || precision == 1, "mmu_knn_tc: precision must be 0 (fp16) or 1 (split fp16)");
+    const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0);
+    const int split = precision != 0;
     MMU_CHECK_ARG(workspace_bytes >= L.total, "mmu_knn_tc: workspace too small (%zu < %zu)", workspace_bytes, L.total);
     MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mmu_knn_tc: workspace must be 256-byte aligned");
     uint8_t *ws = static_cast<uint8_t *>(workspace);
@@ -764,21 +790,23 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         ++launches;
     }
     tc_finish_stats_kernel<<<1, 1024, 0, st>>>(partial, L.stat_blocks, dim, n_db, mean, prm, 1);
-    tc_convert_kernel<<<(unsigned)((L.n_pad * 32 + 255) / 256), 256, 0, st>>>(db, n_db, L.n_pad, dim, L.dim_pad, mean, prm,
-                                                                              db16, ynorm, HUGE_VALF, prm + 1);
+    tc_convert_kernel<<<(unsigned)((L.n_pad * 32 + 255) / 256), 256, 0, st>>>(db, n_db, L.n_pad, dim, L.dim_pad,
+                                                                              split ? 2 : 0, mean, prm, db16, ynorm,
+                                                                              HUGE_VALF, prm + 1);
     launches += 2;
     if (!L.shared_operand) {
         tc_convert_kernel<<<(unsigned)((L.q_pad * 32 + 255) / 256), 256, 0, st>>>(query, n_query, L.q_pad, dim, L.dim_pad,
-                                                                                  mean, prm, q16, xnorm, 0.f, nullptr);
+                                                                                  split ? 1 : 0, mean, prm, q16, xnorm, 0.f,
+                                                                                  nullptr);
         ++launches;
     }
     MMU_LAUNCH_CHECK_N(launches);
 
     // ---- candidates
     CUtensorMap tm_q, tm_db;
-    int rc = make_map(&tm_q, q16, L.q_pad, L.dim_pad, TC_BM);
+    int rc = make_map(&tm_q, q16, L.q_pad, L.width, TC_BM);
     if (rc) return rc;
-    rc = make_map(&tm_db, db16, L.n_pad, L.dim_pad, TC_BN);
+    rc = make_map(&tm_db, db16, L.n_pad, L.width, TC_BN);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -787,7 +815,7 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     }
     TcParams tp;
     tp.ynorm = ynorm;
-    tp.n_kblocks = L.dim_pad / TC_BK;
+    tp.n_kblocks = L.width / TC_BK;
     tp.n_tiles = L.n_tiles;
     tp.tiles_per_split = L.tiles_per_split;
     tp.n_splits = L.n_splits;
@@ -800,12 +828,16 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     // ---- certify + rescore
     RsParams rp;
     rp.query = query; rp.db = db; rp.n_query = n_query; rp.n_db = n_db; rp.dim = dim; rp.k = k;
-    rp.exclude_self = exclude_self; rp.query_index_base = query_index_base;
+    rp.exclude_self = exclude_self; rp.query_index_base = query_index_base; rp.query_gid = query_gid;
     rp.xnorm = xnorm; rp.prm = prm; rp.n_splits = L.n_splits;
     rp.cand_idx = cidx; rp.cand_score = cscore; rp.tau = tau;
     // fp16 rounding of both operands (2 * 2^-11 on each product, x2 for the -2 factor, 1% headroom) plus
     // the fp32 accumulation across dim_pad/16 MMAs and the final fma
     rp.c_rel = 1.01f * 0x1p-9f + ((float)(L.dim_pad / 16) + 16.f) * 0x1p-22f;
+    if (split)   // hi+lo of each operand is exact to 2^-22 relative, the dropped lo.lo term is <= 2^-22 |x||y|; x2 for -2
+        rp.c_rel = 7.0f * 0x1p-22f + ((float)(L.width / 16) + 16.f) * 0x1p-22f;
+    // components below the fp16 subnormal spacing: <= 2^-25 absolute per element and operand, scaled values <= 2^14
+    rp.c_abs = split ? (float)dim * 0x1p-9f : (float)dim * 0x1p-9f;
     rp.c_norm = ((float)(L.dim_pad / 32) + 8.f) * 0x1p-23f;      // lane-strided fma chain + warp tree + final fma
     rp.gamma = ((float)dim + 4.f) * 0x1p-24f;
     rp.out_idx = out_idx; rp.out_dist = out_dist; rp.stats = stats; rp.fallback_rows = fallback_rows;

@@ -44,7 +44,23 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
             int32_t cj = (e < e1) ? col[e] : 0;
             float vj = (e < e1) ? val[e] : 0.f;
             int cnt = (int)min((int64_t)32, e1 - eb);
-            for (int j = 0; j < cnt; ++j) {
+            int j = 0;
+            // four independent gathers in flight per lane (the loop is latency bound otherwise)
+            for (; j + 4 <= cnt; j += 4) {
+                int32_t c0_ = __shfl_sync(0xffffffffu, cj, j), c1_ = __shfl_sync(0xffffffffu, cj, j + 1);
+                int32_t c2_ = __shfl_sync(0xffffffffu, cj, j + 2), c3_ = __shfl_sync(0xffffffffu, cj, j + 3);
+                float v0 = __shfl_sync(0xffffffffu, vj, j), v1 = __shfl_sync(0xffffffffu, vj, j + 1);
+                float v2 = __shfl_sync(0xffffffffu, vj, j + 2), v3 = __shfl_sync(0xffffffffu, vj, j + 3);
+                if (c < m) {
+                    float x0 = x[(int64_t)c0_ * m + c], x1 = x[(int64_t)c1_ * m + c];
+                    float x2 = x[(int64_t)c2_ * m + c], x3 = x[(int64_t)c3_ * m + c];
+                    acc = fmaf(v0, x0, acc);
+                    acc = fmaf(v1, x1, acc);
+                    acc = fmaf(v2, x2, acc);
+                    acc = fmaf(v3, x3, acc);
+                }
+            }
+            for (; j < cnt; ++j) {
                 int32_t cc = __shfl_sync(0xffffffffu, cj, j);
                 float vv = __shfl_sync(0xffffffffu, vj, j);
                 if (c < m) acc = fmaf(vv, x[(int64_t)cc * m + c], acc);

@@ -2,8 +2,11 @@
 
 Role of /root/reference/impl/model.py:81-195 (candidate search + per-row top-k).  The tcgen05
 kernel generates candidates, every row is certified and rescored with the canonical fp32
-distance; rows that cannot be certified are finished by the exhaustive fp32 kernel, so the
-result equals mmu_knn_exact_f32 bit for bit.
+distance.  Rows the first pass cannot certify are retried with a deeper candidate pool (the
+database searched in 8 splits of 64 candidates each) and error-compensated split-fp16 operands
+(hi + lo: error bound 2^-20 |x||y| instead of 2^-9 |x||y|, three times the MMA work); what is still
+uncertified (exact ties beyond the pool, degenerate data) is finished by the exhaustive fp32
+kernel, so the result equals mmu_knn_exact_f32 bit for bit.
 """
 from __future__ import annotations
 
@@ -13,6 +16,23 @@ from . import native
 from .native import check, lib, ptr, stream
 
 last_stats: dict = {}
+DEEP_SPLITS = 8
+
+
+def _call(query, db, k, exclude_self, query_base, gid, same, min_splits, precision=0):
+    q, d = query.shape
+    n = db.shape[0]
+    dev = db.device
+    ws_bytes = lib().mmu_knn_tc_workspace_bytes(q, n, d, int(same), min_splits, precision)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    idx = torch.empty((q, k), dtype=torch.int32, device=dev)
+    dist = torch.empty((q, k), dtype=torch.float32, device=dev)
+    stats = torch.empty(4, dtype=torch.int32, device=dev)
+    fallback = torch.empty(max(q, 1), dtype=torch.int32, device=dev)
+    check(lib().mmu_knn_tc(ptr(query), q, ptr(db), n, d, k, int(exclude_self), query_base, ptr(gid), int(same), min_splits,
+                           precision, ptr(ws), ws_bytes, ptr(idx), ptr(dist), ptr(stats), ptr(fallback), stream()), "mmu_knn_tc")
+    st = stats.tolist()                                   # one small D2H read; the only sync of the call
+    return idx, dist, st, fallback
 
 
 def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, query_base: int = 0):
@@ -24,24 +44,40 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
     db = db.detach().to("cuda", torch.float32).contiguous()
     query = db if same else query.detach().to("cuda", torch.float32).contiguous()
     same = same and query_base == 0
-    q, d = query.shape
+    q = query.shape[0]
     n = db.shape[0]
-    dev = db.device
-    ws_bytes = lib().mmu_knn_tc_workspace_bytes(q, n, d, int(same))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    idx = torch.empty((q, k), dtype=torch.int32, device=dev)
-    dist = torch.empty((q, k), dtype=torch.float32, device=dev)
-    stats = torch.empty(4, dtype=torch.int32, device=dev)
-    fallback = torch.empty(max(q, 1), dtype=torch.int32, device=dev)
-    check(lib().mmu_knn_tc(ptr(query), q, ptr(db), n, d, k, int(exclude_self), query_base, int(same), ptr(ws), ws_bytes,
-                           ptr(idx), ptr(dist), ptr(stats), ptr(fallback), stream()), "mmu_knn_tc")
-    st = stats.tolist()                                   # one small D2H read; the only sync of the call
-    n_fb = int(st[0])
+    # candidate pool depth: one 64-entry list certifies k <= 16 comfortably; deeper pools for larger k
+    min_splits = 0 if k <= 16 else 2
+    precision = 0
+    if q >= 65536 and n >= 65536 and (k > 16 or query.shape[1] <= 256):
+        # probe a strided sample of rows: when the data's neighbourhood gaps are small against the fp16
+        # error bound (low dimension, large N, large norms), go straight to the deep pool for all rows
+        step = q // 2048
+        rows = torch.arange(0, q, step, device=db.device, dtype=torch.int64)[:2048]
+        gid = (rows + query_base).to(torch.int32)
+        _, _, pst, _ = _call(query.index_select(0, rows), db, k, exclude_self, 0, gid, False, min_splits)
+        if pst[0] > 0.1 * rows.numel():
+            min_splits, precision = DEEP_SPLITS, 1
+    idx, dist, st, fallback = _call(query, db, k, exclude_self, query_base, None, same, min_splits, precision)
+    n_fb = n_first = int(st[0])
+    rescored, certified = st[1], st[2]
+    if n_fb and precision == 0:
+        # second level: only the uncertified rows, database in 8 splits (512 candidates per row), split operands
+        rows = fallback[:n_fb].long()
+        gid = (rows + query_base).to(torch.int32)
+        idx2, dist2, st2, fb2 = _call(query.index_select(0, rows), db, k, exclude_self, 0, gid, False, DEEP_SPLITS, 1)
+        idx.index_copy_(0, rows, idx2)
+        dist.index_copy_(0, rows, dist2)
+        n_fb = int(st2[0])
+        rescored, certified = rescored + st2[1], certified + st2[2]
+        fallback = rows.index_select(0, fb2[:n_fb].long()).to(torch.int32) if n_fb else fallback
     if n_fb:
-        # rows the error bound could not certify: exhaustive fp32 search of just those rows
-        check(lib().mmu_knn_exact_f32(ptr(query), n_fb, ptr(fallback), ptr(db), n, d, k, int(exclude_self), query_base,
-                                      0, 0, ptr(idx), ptr(dist), stream()), "mmu_knn_exact_f32(fallback)")
+        # rows no candidate pool can certify (exact ties beyond the pool, degenerate data): exhaustive fp32
+        fallback = fallback[:n_fb].contiguous()
+        check(lib().mmu_knn_exact_f32(ptr(query), n_fb, ptr(fallback), ptr(db), n, query.shape[1], k, int(exclude_self),
+                                      query_base, 0, 0, ptr(idx), ptr(dist), stream()), "mmu_knn_exact_f32(fallback)")
     last_stats.clear()
-    last_stats.update(rows=q, fallback_rows=n_fb, certified_rows=int(st[2]),
-                      rescored_per_row=(st[1] / st[2]) if st[2] else 0.0)
+    last_stats.update(rows=q, first_pass_uncertified=n_first, fallback_rows=n_fb, certified_rows=int(certified),
+                      rescored_per_row=(rescored / certified) if certified else 0.0, min_splits=min_splits,
+                      precision=precision)
     return idx, dist

@@ -136,3 +136,20 @@ def test_database_ring_emulated_on_one_gpu():
             best = (oi, od)
     oi, od = orc.knn_exact(x, x, k, True)
     _same(best[0].cpu().numpy(), best[1].cpu().numpy(), oi[q_lo:q_hi], od[q_lo:q_hi])
+
+
+def test_deep_candidate_pool_certifies_what_one_list_cannot():
+    """Low dimension, k=30, dense neighbourhoods: the gap between the 30th and the 64th neighbour is
+    below the fp16 error bound, so the first pass leaves rows uncertified; the retry with the
+    database in 8 splits (512 candidates per row) and error-compensated split-fp16 operands must
+    certify them -- and the result must still equal the exhaustive kernel bit for bit."""
+    from umap_b200 import graph as G
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, d, k = 60000, 16, 30
+    x = (5.0 * torch.randn((20, d), generator=g, device="cuda")[torch.arange(n, device="cuda") % 20]
+         + torch.randn((n, d), generator=g, device="cuda")).contiguous()
+    ti, td, st = _tc(x, x, k, True)
+    si, sd = G.knn_exact_simt(x, x, k, True)
+    _same(ti, td, si.cpu().numpy(), sd.cpu().numpy())
+    assert st["first_pass_uncertified"] > 0.02 * n or st["precision"] == 1, st      # the fp16 pass alone is not enough here
+    assert st["fallback_rows"] < 0.001 * n, st                                       # ... the split-fp16 deep pool is
