@@ -33,13 +33,15 @@ constexpr int TC_BM = 128;        // query rows per CTA (= TMEM lanes)
 constexpr int TC_BN = 256;        // db rows per tile (= UMMA N, TMEM columns per accumulator)
 constexpr int TC_BK = 64;         // fp16 elements per k-block: 128 bytes = one swizzle span
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 256;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
-constexpr int TC_KP = 64;         // candidates kept per row and db split
+constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
+constexpr int TC_EPI_GROUPS = 2;  // epilogue warps per TMEM lane quarter; group g scans columns [128g, 128g+128) of a tile
+constexpr int TC_KP = 64;         // candidates kept per row and db split (TC_EPI_GROUPS lists of TC_KPG)
+constexpr int TC_KPG = TC_KP / TC_EPI_GROUPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_CH = 16;         // accumulator columns scanned per epilogue step
-constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4 + TC_CH * TC_BM * 4;   // slots + group maxima + scan buffer
+constexpr int TC_CH = 8;          // accumulator columns scanned per epilogue step
+constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4 + TC_EPI_GROUPS * TC_CH * TC_BM * 4;   // slots + group maxima + scan buffers
 constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int RS_PMAX = 128;      // most candidates rescored per row
@@ -108,6 +110,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
         : "r"(taddr)
         : "memory");
 }
@@ -225,7 +234,7 @@ tc_convert_kernel(const float *__restrict__ x, int64_t n, int64_t n_pad, int dim
 // every group cached in `gmax`.  The owner thread keeps the list maximum `tau` and its group
 // `gstar` in registers.  Replacing the maximum costs two rounds of independent loads (the 8 slots
 // of one group, then the 8 group maxima) instead of a pointer-chasing heap walk.
-constexpr int TC_GROUPS = TC_KP / 8;
+constexpr int TC_GROUPS = TC_KPG / 8;                // 8-slot groups per list
 __device__ __forceinline__ void list_replace_max(float *__restrict__ sc, int32_t *__restrict__ id,
                                                  float *__restrict__ gmax, float s, int32_t j, float &tau, int &gstar) {
     float e[8];
@@ -261,7 +270,7 @@ struct TcParams {
     int n_splits;
     int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
     float *cand_score;       // same layout
-    float *tau;              // [n_qblocks][n_splits][128]
+    float *tau;              // [n_qblocks][n_splits][TC_EPI_GROUPS][128]
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -274,7 +283,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     float *list_sc = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
     int32_t *list_id = reinterpret_cast<int32_t *>(list_sc + TC_KP * TC_BM);
     float *list_gmax = reinterpret_cast<float *>(list_id + TC_KP * TC_BM);
-    float *scan_buf = list_gmax + TC_GROUPS * TC_BM;
+    float *scan_buf = list_gmax + (TC_KP / 8) * TC_BM;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES);
     uint64_t *full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
     uint64_t *empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
@@ -295,7 +304,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * TC_EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -352,26 +361,31 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         }
     } else if (warp >= 4) {
         // ===== epilogue: fused per-row top-K' =====
+        // Two warps per TMEM lane quarter: group g of a quarter scans columns [128g, 128g+128) of every tile
+        // into its own TC_KPG-slot list (slots [g*TC_KPG, (g+1)*TC_KPG) of the row).  A row's candidates are
+        // the union of its lists and tau = min over them is still a bound for every non-candidate.
         const int quarter = warp & 3;                  // TMEM lanes 32*quarter .. +31
+        const int grp = (warp - 4) >> 2;
         const int row = quarter * 32 + lane;
-        float *sc = list_sc + row;
-        int32_t *id = list_id + row;
-        float *gmax = list_gmax + row;
-        float *sq = scan_buf + row;
-        for (int s = 0; s < TC_KP; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
+        float *sc = list_sc + grp * TC_KPG * TC_BM + row;
+        int32_t *id = list_id + grp * TC_KPG * TC_BM + row;
+        float *gmax = list_gmax + grp * TC_GROUPS * TC_BM + row;
+        float *sq = scan_buf + grp * TC_CH * TC_BM + row;
+        for (int s = 0; s < TC_KPG; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
         for (int g = 0; g < TC_GROUPS; ++g) gmax[g * TC_BM] = F_INF;
         float tau = F_INF;
         int gstar = 0;
+        constexpr int COLS = TC_BN / TC_EPI_GROUPS;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int acc = it & 1;
-            const int n0 = (t0 + it) * TC_BN;
+            const int n0 = (t0 + it) * TC_BN + grp * COLS;
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN + grp * COLS;
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / TC_CH; ++c) {
+            for (int c = 0; c < COLS / TC_CH; ++c) {
                 uint32_t v[TC_CH];
-                tmem_ld_32x16(taddr + c * TC_CH, v);
+                tmem_ld_32x8(taddr + c * TC_CH, v);
                 float4 yn[TC_CH / 4];
                 const float4 *yp = reinterpret_cast<const float4 *>(p.ynorm + n0 + c * TC_CH);
 #pragma unroll
@@ -401,12 +415,12 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
         // flush: [qblock][split][slot][row] keeps the stores coalesced
-        const int64_t base = ((int64_t)qblock * p.n_splits + split) * TC_KP * TC_BM;
-        for (int s = 0; s < TC_KP; ++s) {
+        const int64_t base = (((int64_t)qblock * p.n_splits + split) * TC_KP + grp * TC_KPG) * TC_BM;
+        for (int s = 0; s < TC_KPG; ++s) {
             p.cand_idx[base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
             p.cand_score[base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
         }
-        p.tau[((int64_t)qblock * p.n_splits + split) * TC_BM + row] = tau;
+        p.tau[(((int64_t)qblock * p.n_splits + split) * TC_EPI_GROUPS + grp) * TC_BM + row] = tau;
     }
 
     tc_fence_before();
@@ -486,7 +500,8 @@ knn_tc_rescore_kernel(const RsParams p) {
             if (j >= 0 && j < p.n_db && !self) { cs[u] = s; ci[u] = j; }
         }
     }
-    for (int s = lane; s < p.n_splits; s += 32) tau = fminf(tau, p.tau[((int64_t)qblock * p.n_splits + s) * TC_BM + r]);
+    for (int s = lane; s < p.n_splits * TC_EPI_GROUPS; s += 32)
+        tau = fminf(tau, p.tau[((int64_t)qblock * p.n_splits * TC_EPI_GROUPS + s) * TC_BM + r]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
 
@@ -731,7 +746,7 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     size_t cand = (size_t)L.n_qblocks * L.n_splits * TC_KP * TC_BM;
     L.off_cidx = o; o += align256(sizeof(int32_t) * cand);
     L.off_cscore = o; o += align256(sizeof(float) * cand);
-    L.off_tau = o; o += align256(sizeof(float) * (size_t)L.n_qblocks * L.n_splits * TC_BM);
+    L.off_tau = o; o += align256(sizeof(float) * (size_t)L.n_qblocks * L.n_splits * TC_EPI_GROUPS * TC_BM);
     L.total = o;
     return L;
 }
