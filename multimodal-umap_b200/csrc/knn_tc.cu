@@ -268,6 +268,7 @@ struct TcParams {
     int n_tiles;             // n_db_pad / 256
     int tiles_per_split;
     int n_splits;
+    int split_major;         // grid = (n_splits, n_qblocks): co-resident CTAs share query blocks instead of db tiles
     int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
     float *cand_score;       // same layout
     float *tau;              // [n_qblocks][n_splits][TC_EPI_GROUPS][128]
@@ -292,7 +293,12 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qblock = blockIdx.x, split = blockIdx.y;
+    // rasterisation: x is the fast index of the block scheduler.  Query-block-major (default) keeps ~148
+    // different query blocks and ONE database region in flight -- right while 148 query tiles fit in L2
+    // beside it; for long rows (148 x 128 x D x 2 B of query tiles alone overflow the L2) split-major keeps
+    // few query blocks and all database regions in flight instead.
+    const int qblock = p.split_major ? blockIdx.y : blockIdx.x;
+    const int split = p.split_major ? blockIdx.x : blockIdx.y;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
@@ -837,7 +843,14 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     tp.cand_idx = cidx;
     tp.cand_score = cscore;
     tp.tau = tau;
-    knn_tc_candidates_kernel<<<dim3(L.n_qblocks, L.n_splits), TC_THREADS, TC_SMEM_BYTES, st>>>(tm_q, tm_db, tp);
+    {
+        int sms = sm_count();
+        if (sms <= 0) sms = 148;
+        const size_t q_tiles_in_flight = (size_t)sms * TC_BM * L.width * 2;
+        tp.split_major = (L.n_splits > 1 && q_tiles_in_flight > ((size_t)48 << 20)) ? 1 : 0;
+    }
+    const dim3 grid = tp.split_major ? dim3(L.n_splits, L.n_qblocks) : dim3(L.n_qblocks, L.n_splits);
+    knn_tc_candidates_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_q, tm_db, tp);
     MMU_LAUNCH_CHECK();
 
     // ---- certify + rescore
