@@ -16,6 +16,7 @@ Engine switches (attributes of UMAPMixture / environment):
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 import warnings
@@ -54,6 +55,23 @@ def _coo(g: G.Graph) -> torch.Tensor:
     idx = torch.stack([g.row.long(), g.col.long()], dim=0)
     t = torch.sparse_coo_tensor(idx, g.val, (g.n_rows, g.n_cols), is_coalesced=True)
     return _register(t, g)
+
+
+@functools.lru_cache(maxsize=64)
+def _ab_coeffs(min_dist: float, num_iters: int):
+    """Gauss-Newton fit of model.py:587-618 (a pure function of min_dist: cached per value)."""
+    x = torch.linspace(1e-4, 3.0, 200, dtype=torch.float32)
+    target = torch.where(x <= min_dist, torch.tensor(1.0), torch.exp(-(x - min_dist)))
+    betas = torch.tensor([1.0, 1.0])
+    for _ in range(num_iters):
+        a_, b_ = betas[0].abs() + 1e-6, betas[1].abs() + 1e-6
+        xp = x.pow(2 * b_)
+        est = 1.0 / (1.0 + a_ * xp)
+        res = target - est
+        jac = torch.stack([torch.sign(betas[0]) * xp * est * est,
+                           torch.sign(betas[1]) * a_ * xp * 2.0 * torch.log(x) * est * est], dim=1)
+        betas = betas - torch.linalg.pinv(jac) @ res
+    return (betas[0].abs() + 1e-6).item(), (betas[1].abs() + 1e-6).item()
 
 
 class UMAPEncoder:
@@ -220,18 +238,7 @@ class UMAPMixture:
     def get_ab_coeffs(self, min_dist: float, num_iters: int = 50):
         """ref: model.py:587-618: Gauss-Newton fit of 1/(1+a x^(2b)) to the min_dist target on
         linspace(1e-4, 3, 200) from (1, 1), fp32; closed-form Jacobian instead of autograd."""
-        x = torch.linspace(1e-4, 3.0, 200, dtype=torch.float32)
-        target = torch.where(x <= min_dist, torch.tensor(1.0), torch.exp(-(x - min_dist)))
-        betas = torch.tensor([1.0, 1.0])
-        for _ in range(num_iters):
-            a_, b_ = betas[0].abs() + 1e-6, betas[1].abs() + 1e-6
-            xp = x.pow(2 * b_)
-            est = 1.0 / (1.0 + a_ * xp)
-            res = target - est
-            jac = torch.stack([torch.sign(betas[0]) * xp * est * est,
-                               torch.sign(betas[1]) * a_ * xp * 2.0 * torch.log(x) * est * est], dim=1)
-            betas = betas - torch.linalg.pinv(jac) @ res
-        return (betas[0].abs() + 1e-6).item(), (betas[1].abs() + 1e-6).item()
+        return _ab_coeffs(float(min_dist), int(num_iters))
 
     # ------------------------------------------------------------------ orchestration
     def init(self, inputs: list, mode: str = "fit", data_indices: list | None = None):

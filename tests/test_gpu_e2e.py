@@ -90,3 +90,58 @@ def test_embed_and_recon_runs_and_reconstructs(monkeypatch):
     rng = np.random.default_rng(0)
     base = np.linalg.norm(train_d["images"][rng.integers(0, 1500, true.shape[0])] - true, axis=1).mean()
     assert err < 0.6 * base, (err, base)
+
+
+def test_batched_metrics_equal_the_row_loop():
+    """umap_b200.metrics.retrieval_accuracy (engine kNN, query mode) vs the reference's per-row loop
+    (validation.py:66-78: torch.norm + topk + `idx in knns`) on random embeddings."""
+    from umap_b200 import metrics
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(700, 8, generator=g)
+    b = a + 0.8 * torch.randn(700, 8, generator=g)
+    for k in (1, 5):
+        correct = 0
+        for i in range(a.shape[0]):
+            if i in torch.topk(torch.norm(b - a[i], dim=1), k, largest=False).indices:
+                correct += 1
+            if i in torch.topk(torch.norm(a - b[i], dim=1), k, largest=False).indices:
+                correct += 1
+        want = correct / (2 * a.shape[0])
+        got = metrics.retrieval_accuracy(a, b, k)
+        assert abs(got - want) < 1.5 / a.shape[0], (k, got, want)       # fp32 near-ties may flip a row or two
+
+
+def test_reference_written_checkpoint_loads_and_transforms(golden_dir):
+    """A checkpoint written by the reference's own save_state_dict (int64 sparse COO graphs, CPU leaf
+    embeddings; oracle/make_golden_checkpoint.py) loads through the engine's load_state_dict and
+    serves transform(): the held-out rows land where the reference put them, up to the spread of its
+    own stochastic transform (compared through nearest fitted neighbours, not coordinates)."""
+    model_mod = importlib.import_module("impl.model")
+    util = importlib.import_module("impl.util")
+    path = os.path.join(golden_dir, "ref_checkpoint.pt")
+    model = model_mod.UMAPMixture.load_state_dict(path)
+    assert model.k_neighbors == 10 and model.out_dim == 4 and model.num_encoders == 2
+    assert model.graphs[0].is_sparse and model.graphs[0].indices().dtype == torch.int64
+    ref = np.load(os.path.join(golden_dir, "ref_checkpoint_transform.npz"))
+    from oracle.e2e_data import make_problem as mp
+    _, test_d = mp(n_train=400, n_test=60, clusters=5, seed=77)
+    cfg = util.Config(k_neighbors=10, out_dim=4, min_dist=0.1, train_epochs=150, num_rep=8, lr=0.01, alpha=1.0,
+                      batch_size=128, test_epochs=40)
+    torch.manual_seed(6)
+    out = util.embed(model, [torch.from_numpy(test_d["texts"]), torch.from_numpy(test_d["images"])], [0, 1], cfg)
+    for m, name in enumerate(("texts", "images")):
+        got = out[m].detach().cpu().numpy()
+        assert got.shape == ref[name].shape and np.all(np.isfinite(got))
+        fitted = model.embeds[m].detach().cpu().numpy()
+        # same neighbourhood of the fitted embedding: the nearest fitted row of the engine's placement is
+        # among the 15 nearest fitted rows of the reference's placement for most queries
+        d_ref = np.linalg.norm(ref[name][:, None, :] - fitted[None], axis=2)
+        d_got = np.linalg.norm(got[:, None, :] - fitted[None], axis=2)
+        near_ref = np.argsort(d_ref, axis=1)[:, :15]
+        hit = np.mean([d_got[i].argmin() in near_ref[i] for i in range(got.shape[0])])
+        assert hit > 0.7, (name, hit)
+    # and the engine writes a checkpoint the same loader reads back
+    tmp = os.path.join(os.environ.get("TMPDIR", "/tmp"), "mmu_ckpt_roundtrip.pt")
+    model.save_state_dict(tmp)
+    again = model_mod.UMAPMixture.load_state_dict(tmp)
+    assert torch.equal(again.embeds[0].detach().cpu(), model.embeds[0].detach().cpu())
