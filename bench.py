@@ -275,7 +275,7 @@ def run_b200(args, workload, data):
     if rank == 0:
         sampler.start()
     launches0 = native.lib().mmu_launch_count()
-    profiler.enable(True)
+    profiler.enable(1)            # coarse stages + the force kernel; the small kernels get their own pass below
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     model = None
@@ -286,7 +286,11 @@ def run_b200(args, workload, data):
     total_ms = ev0.elapsed_time(ev1)
     launches = native.lib().mmu_launch_count() - launches0
     stages = profiler.summarize(profiler.collect())
-    profiler.enable(False)
+    # one extra, untimed, fully instrumented fit for the per-kernel breakdown of an epoch
+    profiler.enable(2)
+    fit_resident()
+    fine = profiler.summarize(profiler.collect())
+    profiler.enable(0)
     kept = model.last_optimizer.kept_last_epoch()
     nnz = [int(model.last_optimizer.mods[i].graph.nnz) for i in range(len(model.last_optimizer.mods))]
     rows = [int(m.count) for m in model.last_optimizer.mods]
@@ -378,6 +382,8 @@ def run_b200(args, workload, data):
         "roofline_other": other,
         "stages": {
             "ms": {k: round(v["ms"], 3) for k, v in st.items()},
+            "epoch_kernels_us_per_launch": {k: round(v["ms"] / max(v["calls"], 1) * 1e3, 1) for k, v in fine.items()
+                                            if k in ("edge_sample", "edge_forces", "infonce", "adam")},
             "knn_tflops": knn_tflops,
             "sgd_edge_updates_per_s": edge_updates * epochs / (opt_ms * 1e-3) if opt_ms else None,
             "sgd_gbs": bytes_epoch * epochs / (opt_ms * 1e-3) / 1e9 if opt_ms else None,

@@ -185,6 +185,14 @@ int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, i
                           int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept,
                           mmu_stream_t stream);
 
+/* The same with the epoch number given by the host (epoch >= 0) instead of read from `state`:
+ * lets the sampling of epoch e+1 run on a second stream while the forces of epoch e execute (it
+ * does not depend on the embeddings).  epoch = -1 reads state->epoch. */
+int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
+                       int batch_size, int n_batches, uint64_t seed, int64_t epoch,
+                       const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
+                       int32_t *batch_kept, mmu_stream_t stream);
+
 /* K7b: forces of every kept edge and its num_rep negatives, accumulated with red.global.add
  * into the gradient table(s).  Gradient of
  *   mean_batches[ mean_kept log(1+a s^b) + mean_{kept*R} -log(a s^b/(1+a s^b)+1e-6) ],

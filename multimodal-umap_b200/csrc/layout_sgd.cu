@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(256)
 edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, const float *__restrict__ w,
                    int64_t edge_lo, int64_t nnz, int batch_size, uint64_t seed, const OptState *__restrict__ st,
                    int32_t *__restrict__ kept_pos, int4 *__restrict__ kept_rec, int32_t *__restrict__ kept_count,
-                   int32_t *__restrict__ batch_kept) {
+                   int32_t *__restrict__ batch_kept, int64_t epoch_override) {
     // edges [edge_lo, nnz) of the global COO; the Philox counter is the GLOBAL quad index, so a
     // shard draws exactly what the single-GPU run draws for the same edges
-    const uint32_t epoch = st->epoch;
+    const uint32_t epoch = epoch_override >= 0 ? (uint32_t)epoch_override : st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n4 = (nnz + 3) >> 2;
@@ -820,9 +820,20 @@ extern "C" int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, d
     return MMU_OK;
 }
 
+extern "C" int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi, int batch_size,
+                                  int n_batches, uint64_t seed, int64_t epoch, const uint32_t *state, int32_t *kept_pos,
+                                  int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream);
+
 extern "C" int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
                                      int batch_size, int n_batches, uint64_t seed, const uint32_t *state,
                                      int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream) {
+    return mmu_edge_sample_at(row, w, edge_lo, edge_hi, batch_size, n_batches, seed, -1, state, kept_pos, kept_count,
+                              batch_kept, stream);
+}
+
+extern "C" int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi, int batch_size,
+                                  int n_batches, uint64_t seed, int64_t epoch, const uint32_t *state, int32_t *kept_pos,
+                                  int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(row && w && state && kept_pos && kept_count && batch_kept, "mmu_edge_sample: null pointer");
     MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample: bad batch geometry");
@@ -837,7 +848,7 @@ extern "C" int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
     edge_sample_kernel<false><<<blocks, 256, 0, st>>>(row, nullptr, w, edge_lo, edge_hi, batch_size, seed,
                                                       reinterpret_cast<const OptState *>(state), kept_pos, nullptr,
-                                                      kept_count, batch_kept);
+                                                      kept_count, batch_kept, epoch);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
@@ -861,7 +872,7 @@ extern "C" int mmu_edge_sample_records(const int32_t *row, const int32_t *col, c
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
     edge_sample_kernel<true><<<blocks, 256, 0, st>>>(row, col, w, edge_lo, edge_hi, batch_size, seed,
                                                      reinterpret_cast<const OptState *>(state), nullptr,
-                                                     reinterpret_cast<int4 *>(kept_rec), kept_count, batch_kept);
+                                                     reinterpret_cast<int4 *>(kept_rec), kept_count, batch_kept, -1);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

@@ -57,6 +57,39 @@ def _coo(g: G.Graph) -> torch.Tensor:
     return _register(t, g)
 
 
+class _Uploads:
+    """Device copies of a list of inputs.  Host tensors are copied on a side stream in list order, so the
+    upload of modality i+1 overlaps the graph construction of modality i (pinned host memory makes the
+    copies asynchronous); indexing waits for that tensor's copy only."""
+
+    def __init__(self, inputs):
+        native.require_cuda()                      # no CPU fallback: fail before touching any stream
+        self._items = []
+        side = None
+        for x in inputs:
+            if x.is_cuda:
+                self._items.append((x, None))
+                continue
+            if side is None:
+                side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                t = x.to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            self._items.append((t, ev))
+
+    def __len__(self):
+        return len(self._items)
+
+    def __getitem__(self, i):
+        t, ev = self._items[i]
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            t.record_stream(torch.cuda.current_stream())
+            self._items[i] = (t, None)
+        return t
+
+
 @functools.lru_cache(maxsize=64)
 def _ab_coeffs(min_dist: float, num_iters: int):
     """Gauss-Newton fit of model.py:587-618 (a pure function of min_dist: cached per value)."""
@@ -203,10 +236,12 @@ class UMAPMixture:
 
     def fit(self, inputs: list, epochs: int, num_rep: int = 8, lr: float = 0.2, alpha: float = 0.5,
             batch_size: int = 512) -> None:
-        """ref: model.py:483-508."""
+        """ref: model.py:483-508.  (The reference uploads the inputs twice, :496 and :634; here the device
+        copies made for the graph stage are the ones kept as self.data.)"""
+        inputs = _Uploads(inputs)
         graphs, embeds = self.init(inputs, mode="fit")
         self.graphs = graphs
-        self.data = [x.to(device) for x in inputs]
+        self.data = [inputs[i] for i in range(len(inputs))]
         self.embeds = self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="fit",
                                   desc=f"Training {self.num_encoders} encoders")
 
@@ -246,7 +281,8 @@ class UMAPMixture:
         if mode not in ["fit", "transform", "invert"]:
             raise ValueError(f"Invalid mode: {mode}")
         native.require_cuda()
-        inputs = [x.to(device) for x in inputs]
+        if not isinstance(inputs, _Uploads):
+            inputs = _Uploads(inputs)
         graphs, embeds = [], []
         encoder_indices = data_indices if data_indices is not None else range(self.num_encoders)
         for idx, i in enumerate(encoder_indices):

@@ -151,6 +151,7 @@ class LayoutOptimizer:
                             and all(lib().mmu_edge_forces_records_supported(m.dim, self.num_rep) for m in self.mods))
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
         self.losses: list[float] = []
+        self.done = 0                  # epochs completed (== the device-side epoch counter)
         self.edge_updates = 0          # host-stream mode counts them exactly; device mode reads kept_count
 
     # ------------------------------------------------------------------ one epoch
@@ -217,7 +218,7 @@ class LayoutOptimizer:
                 g = mod.graph
                 if mod.kept_rec is None:
                     mod.kept_rec = torch.empty((max(mod.e_hi - mod.e_lo, 1), 4), dtype=torch.int32, device=dev)
-                with profiler.stage("edge_sample"):
+                with profiler.stage("edge_sample", level=2):
                     check(lib().mmu_edge_sample_records(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi,
                                                         mod.batch_size, mod.n_batches, self.seed, ptr(self.state),
                                                         ptr(mod.kept_rec), ptr(mod.kept_count), ptr(mod.batch_kept),
@@ -225,12 +226,18 @@ class LayoutOptimizer:
                 self._forces(mod, None, mod.kept_count, None, mod.batch_kept)
             else:
                 g = mod.graph
-                with profiler.stage("edge_sample"):
+                with profiler.stage("edge_sample", level=2):
                     check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
                                                       mod.n_batches, self.seed, ptr(self.state), ptr(mod.kept_pos),
                                                       ptr(mod.kept_count), ptr(mod.batch_kept), stream()),
                           "mmu_edge_sample_range")
                 self._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
+        self._epoch_tail()
+
+    def _epoch_tail(self):
+        """InfoNCE, gradient all-reduce, Adam: everything of an epoch after the force kernels."""
+        host = self.sample_stream == "host"
+        dev = torch.device("cuda")
         if self.mode == "fit":                                           # model.py:459-472
             n = len(self.mods)
             sid = 0
@@ -247,7 +254,7 @@ class LayoutOptimizer:
                         (pf, nf), (pr, nr) = replay_infonce_draws(num), replay_infonce_draws(num)
                         pf, nf, pr, nr = (t.pin_memory().to(dev, non_blocking=True) for t in (pf, nf, pr, nr))
                     # both directions in one grid: they read the same embedding state
-                    with profiler.stage("infonce"):
+                    with profiler.stage("infonce", level=2):
                         check(lib().mmu_infonce_bidir(ptr(src.p), ptr(dst.p), num, a_lo, a_hi, src.dim, ptr(pf), ptr(nf),
                                                       ptr(pr), ptr(nr), INFONCE_NEG, INFONCE_CHUNK, self.alpha, INFONCE_TAU,
                                                       ptr(src.g), ptr(dst.g), self.seed, sid, ptr(self.state),
@@ -257,13 +264,61 @@ class LayoutOptimizer:
         D.all_reduce_sum(self.flat[1])
         check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
         p, g, m, v = self.flat
-        with profiler.stage("adam"):
+        with profiler.stage("adam", level=2):
             check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
                                       stream()), "mmu_adam_step")
+        self.done += 1
         if self.loss is not None:
             D.all_reduce_sum(self.loss)
             self.losses.append(float(self.loss.item()))
             self.loss.zero_()
+
+    def _run_overlapped(self, epochs: int):
+        """Device sample stream, large problems: the Bernoulli sampling of epoch e+1 does not depend on the
+        embeddings, so it runs on a second stream (double-buffered kept lists, explicit epoch number) while
+        the force kernels of epoch e execute; the main stream only waits for the sampled-event."""
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        dev = torch.device("cuda")
+        bufs = []
+        for mod in self.mods:
+            bufs.append([(mod.kept_pos, mod.kept_count, mod.batch_kept),
+                         (torch.empty_like(mod.kept_pos), torch.zeros_like(mod.kept_count), torch.zeros_like(mod.batch_kept))])
+        sampled = [None, None]
+        consumed = [None, None]
+        base = self.done
+
+        def issue_sample(e):
+            b = e & 1
+            with torch.cuda.stream(side):
+                if consumed[b] is not None:
+                    side.wait_event(consumed[b])
+                for mi, mod in enumerate(self.mods):
+                    g = mod.graph
+                    kp, kc, bk = bufs[mi][b]
+                    check(lib().mmu_edge_sample_at(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size, mod.n_batches,
+                                                   self.seed, base + e, ptr(self.state), ptr(kp), ptr(kc), ptr(bk),
+                                                   side.cuda_stream), "mmu_edge_sample_at")
+                ev = torch.cuda.Event()
+                ev.record(side)
+                sampled[b] = ev
+
+        issue_sample(0)
+        for e in range(epochs):
+            if e + 1 < epochs:
+                issue_sample(e + 1)
+            b = e & 1
+            main.wait_event(sampled[b])
+            for mi, mod in enumerate(self.mods):
+                kp, kc, bk = bufs[mi][b]
+                mod.kept_count = kc                      # kept_last_epoch() reads the buffer in use
+                self._forces(mod, kp, kc, None, bk)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            consumed[b] = ev
+            self._epoch_tail()
+        main.wait_stream(side)
 
     def run(self, epochs: int):
         """`epochs` optimiser epochs.  With the device sample stream an epoch is a fixed sequence of
@@ -276,8 +331,13 @@ class LayoutOptimizer:
                      and (mode == "1" or (mode == "auto" and small))
                      and (D.world() == 1 or os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1"))
         if not use_graph:
-            for _ in range(epochs):
-                self.epoch()
+            overlap = (self.sample_stream == "device" and not self.use_records and self.mode in ("fit", "transform")
+                       and epochs > 1 and os.environ.get("MMUMAP_OVERLAP_SAMPLE", "1") == "1")
+            if overlap:
+                self._run_overlapped(epochs)
+            else:
+                for _ in range(epochs):
+                    self.epoch()
             return self.result()
         self.epoch()                                   # eager first epoch: loads every kernel before capture
         graph = torch.cuda.CUDAGraph()

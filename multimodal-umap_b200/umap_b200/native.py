@@ -54,6 +54,8 @@ _SIGNATURES = {
                                 c_void_p, c_void_p]),
     "mmu_edge_sample_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_sample_at": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
     "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
                                 c_void_p, c_void_p, c_int, c_void_p]),

@@ -11,23 +11,25 @@ from contextlib import contextmanager
 
 import torch
 
-_enabled = False
+_level = 0
 _records: list = []
 
 
-def enable(flag: bool = True) -> None:
-    global _enabled
-    _enabled = flag
+def enable(level: int | bool = 1) -> None:
+    """0/False: off.  1: coarse stages + the dominant kernel (cheap enough for a timed region).
+    2: additionally every small per-epoch kernel (a few microseconds of event overhead per launch)."""
+    global _level
+    _level = int(level)
     _records.clear()
 
 
-def enabled() -> bool:
-    return _enabled
+def enabled(level: int = 1) -> bool:
+    return _level >= level
 
 
 @contextmanager
-def stage(name: str, **meta):
-    if not _enabled:
+def stage(name: str, level: int = 1, **meta):
+    if _level < level:
         yield
         return
     start = torch.cuda.Event(enable_timing=True)

@@ -26,7 +26,7 @@ e0.record(); opt.run(E); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / E
 kept = opt.kept_last_epoch()
 from umap_b200 import profiler
-profiler.enable(True)
+profiler.enable(2)
 opt.run(50)
 for k, v in profiler.summarize(profiler.collect()).items():
     print(f"   {k:14s} {v['ms']/v['calls']*1e3:8.1f} us/launch x {v['calls']//50}/epoch")
