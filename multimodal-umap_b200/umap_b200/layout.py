@@ -339,6 +339,7 @@ class LayoutOptimizer:
                 for _ in range(epochs):
                     self.epoch()
             return self.result()
+        start = self.done
         self.epoch()                                   # eager first epoch: loads every kernel before capture
         graph = torch.cuda.CUDAGraph()
         before = lib().mmu_launch_count()
@@ -358,6 +359,7 @@ class LayoutOptimizer:
         lib().mmu_launch_count_add((epochs - 2) * per_epoch)      # the capture pass itself counted once
         for _ in range(epochs - 1):
             graph.replay()
+        self.done = start + epochs                     # the capture pass counted itself without executing
         self._graph = graph                            # keep alive until the stream has drained
         return self.result()
 
