@@ -679,14 +679,26 @@ infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_,
             if (m < M) ids[m] = neg[tt * n_neg + (m - 1)];
     } else {
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        Philox4 rnd = {0, 0, 0, 0};
+        constexpr int NCALL = (MCAP - 1 + 3) / 4;
+        if (MT && LANES >= NCALL) {
+            // lane c of the group evaluates Philox call c (same counters, same draws as the serial form)
+            const Philox4 w = philox4x32_10((uint32_t)tt, (uint32_t)(gl % NCALL), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
 #pragma unroll
-        for (int m = 1; m < MCAP; ++m) {
-            if (m >= M) continue;
-            int q = m - 1;
-            if ((q & 3) == 0) rnd = philox4x32_10((uint32_t)tt, (uint32_t)(q >> 2), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
-            uint32_t x = (q & 3) == 0 ? rnd.x : (q & 3) == 1 ? rnd.y : (q & 3) == 2 ? rnd.z : rnd.w;
-            ids[m] = (int32_t)urange(x, (uint32_t)num);
+            for (int m = 1; m < MCAP; ++m) {
+                const int q = m - 1;
+                const uint32_t mine = (q & 3) == 0 ? w.x : (q & 3) == 1 ? w.y : (q & 3) == 2 ? w.z : w.w;
+                ids[m] = (int32_t)urange(__shfl_sync(0xffffffffu, mine, q >> 2, LANES), (uint32_t)num);
+            }
+        } else {
+            Philox4 rnd = {0, 0, 0, 0};
+#pragma unroll
+            for (int m = 1; m < MCAP; ++m) {
+                if (m >= M) continue;
+                int q = m - 1;
+                if ((q & 3) == 0) rnd = philox4x32_10((uint32_t)tt, (uint32_t)(q >> 2), st->epoch, STREAM_INFONCE + stream_id, k0, k1);
+                uint32_t x = (q & 3) == 0 ? rnd.x : (q & 3) == 1 ? rnd.y : (q & 3) == 2 ? rnd.z : rnd.w;
+                ids[m] = (int32_t)urange(x, (uint32_t)num);
+            }
         }
     }
     const Vec<VEC> av = load_vec<VEC>(e0 + (int64_t)i * DIM + gl * VEC);
