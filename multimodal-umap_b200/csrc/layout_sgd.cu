@@ -712,7 +712,10 @@ infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_,
 #pragma unroll
     for (int c = 0; c < VEC; ++c) na2 = fmaf(av.v[c], av.v[c], na2);
     const float na = fmaxf(sqrtf(group_sum<LANES>(na2)), 1e-12f);       // F.normalize eps
-    float nrm[MCAP], cs[MCAP];
+    // one reciprocal per quantity instead of a division per use (the kernel is instruction bound)
+    const float inv_t = 1.0f / temperature;
+    const float inv_na = 1.0f / na;
+    float inv_nrm[MCAP], cs[MCAP], ex[MCAP];
     float mx = -__int_as_float(0x7f800000);
 #pragma unroll
     for (int m = 0; m < MCAP; ++m) {
@@ -724,30 +727,33 @@ infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_,
         for (int c = 0; c < VEC; ++c) { n2 = fmaf(ev.v[c], ev.v[c], n2); dt = fmaf(av.v[c], ev.v[c], dt); }
         n2 = group_sum<LANES>(n2);
         dt = group_sum<LANES>(dt);
-        nrm[m] = fmaxf(sqrtf(n2), 1e-12f);
-        cs[m] = dt / (na * nrm[m]);
-        if (ok) mx = fmaxf(mx, cs[m] / temperature);
+        inv_nrm[m] = 1.0f / fmaxf(sqrtf(n2), 1e-12f);
+        cs[m] = dt * inv_na * inv_nrm[m];
+        if (ok) mx = fmaxf(mx, cs[m] * inv_t);
     }
     float den = 0.f;
 #pragma unroll
     for (int m = 0; m < MCAP; ++m)
-        if (m < M && (m == 0 || ids[m] != i)) den += expf(cs[m] / temperature - mx);
-    float loss_local = (active && gl == 0) ? wgt * -(cs[0] / temperature - mx - logf(den)) : 0.f;
+        if (m < M) {
+            ex[m] = (m == 0 || ids[m] != i) ? expf(fmaf(cs[m], inv_t, -mx)) : 0.f;
+            den += ex[m];
+        }
+    const float inv_den = 1.0f / den;
+    float loss_local = (active && gl == 0) ? wgt * -(fmaf(cs[0], inv_t, -mx) - logf(den)) : 0.f;
     float ccs = 0.f;
     Vec<VEC> acc;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc.v[c] = 0.f;
-    const float inv_na = 1.0f / na;
 #pragma unroll
     for (int m = 0; m < MCAP; ++m) {
         if (m >= M) continue;
         const bool ok = m == 0 || ids[m] != i;
         if (!ok) continue;                                               // group-uniform
-        const float cm = expf(cs[m] / temperature - mx) / den - (m == 0 ? 1.f : 0.f);
+        const float cm = ex[m] * inv_den - (m == 0 ? 1.f : 0.f);
         ccs = fmaf(cm, cs[m], ccs);
         const Vec<VEC> ev = MT ? evr[MT ? m : 0] : load_vec<VEC>(e1 + (int64_t)ids[m] * DIM + gl * VEC);
-        const float inv_n = 1.0f / nrm[m];
-        const float sm = wgt * cm / (temperature * nrm[m]);
+        const float inv_n = inv_nrm[m];
+        const float sm = wgt * cm * inv_t * inv_n;
         Vec<VEC> g;
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
@@ -757,7 +763,7 @@ infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_,
         }
         if (active) red_vec<VEC>(grad1 + (int64_t)ids[m] * DIM + gl * VEC, g, 1.0f);
     }
-    const float sa = wgt / (temperature * na);
+    const float sa = wgt * inv_t * inv_na;
     Vec<VEC> ga;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) ga.v[c] = sa * (acc.v[c] - av.v[c] * inv_na * ccs);   // d/d a
