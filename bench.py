@@ -286,6 +286,9 @@ def run_b200(args, workload, data):
     total_ms = ev0.elapsed_time(ev1)
     launches = native.lib().mmu_launch_count() - launches0
     stages = profiler.summarize(profiler.collect())
+    if os.environ.get("MMUMAP_BENCH_DEBUG") == "1":
+        print(f"[rank {rank}] stages ms/step: " + ", ".join(f"{k}={v['ms'] / args.steps:.1f}" for k, v in stages.items()),
+              file=sys.stderr, flush=True)
     # one extra, untimed, fully instrumented fit for the per-kernel breakdown of an epoch
     profiler.enable(2)
     fit_resident()

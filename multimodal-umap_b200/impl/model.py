@@ -285,6 +285,8 @@ class UMAPMixture:
             inputs = _Uploads(inputs)
         graphs, embeds = [], []
         encoder_indices = data_indices if data_indices is not None else range(self.num_encoders)
+        if mode == "fit" and D.world() > 1:
+            return self._init_fit_distributed(inputs, list(encoder_indices))
         for idx, i in enumerate(encoder_indices):
             encoder = self.encoders[i]
             if mode == "fit":
@@ -298,6 +300,32 @@ class UMAPMixture:
                                             ref_data=self.graphs[i], ref_embeds=self.data[i], a=self.a, b=self.b)
             graphs.append(graph)
             embeds.append(embed)
+        return graphs, embeds
+
+    def _init_fit_distributed(self, inputs, encoder_indices):
+        """Multi-GPU form of the fit initialisation: all graphs first (row-sharded kNN + replicated
+        sigma/union), then every rank solves the spectral problems it owns (modality m -> rank m mod W)
+        concurrently, then the results are broadcast -- instead of serialising the solves behind each
+        other's broadcasts."""
+        graphs, syms = [], []
+        for idx, i in enumerate(encoder_indices):
+            enc = self.encoders[i]
+            graph = enc.fuzzy_knn_graph(inputs[idx], "fit", None, None, num_iters=10)
+            g = _as_graph(graph)
+            with profiler.stage("fuzzy_union"):
+                sym = G.fuzzy_union(g.col2d, g.w2d)                      # model.py:271
+            syms.append(sym)
+            graphs.append(_coo(sym))
+        embeds = [None] * len(encoder_indices)
+        with profiler.stage("spectral_init"):
+            for idx, i in enumerate(encoder_indices):
+                if D.rank() == self.encoders[i].id % D.world():
+                    embeds[idx] = spectral_init(syms[idx], self.out_dim).contiguous()
+            for idx, i in enumerate(encoder_indices):
+                owner = self.encoders[i].id % D.world()
+                if embeds[idx] is None:
+                    embeds[idx] = torch.empty((syms[idx].n_rows, self.out_dim), dtype=torch.float32, device="cuda")
+                D.broadcast(embeds[idx], owner)
         return graphs, embeds
 
     # ------------------------------------------------------------------ checkpoint

@@ -68,14 +68,17 @@ def knn_sharded_rows(x: torch.Tensor, k: int, exclude_self: bool, knn_fn):
     per = block_size(n, w)
     idx_pad = torch.full((per, k), -1, dtype=torch.int32, device=x.device)
     dist_pad = torch.full((per, k), float("inf"), dtype=torch.float32, device=x.device)
+    from . import profiler
     if hi > lo:
-        idx_l, dist_l = knn_fn(x[lo:hi], x, k, exclude_self, lo)
+        with profiler.stage("knn_local"):
+            idx_l, dist_l = knn_fn(x[lo:hi], x, k, exclude_self, lo)
         idx_pad[: hi - lo] = idx_l
         dist_pad[: hi - lo] = dist_l
     idx_all = torch.empty((w * per, k), dtype=torch.int32, device=x.device)
     dist_all = torch.empty((w * per, k), dtype=torch.float32, device=x.device)
-    dist.all_gather_into_tensor(idx_all, idx_pad)
-    dist.all_gather_into_tensor(dist_all, dist_pad)
+    with profiler.stage("knn_allgather"):
+        dist.all_gather_into_tensor(idx_all, idx_pad)
+        dist.all_gather_into_tensor(dist_all, dist_pad)
     return idx_all[:n].contiguous(), dist_all[:n].contiguous()
 
 
