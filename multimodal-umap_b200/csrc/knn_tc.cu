@@ -40,8 +40,8 @@ constexpr int TC_KPG = TC_KP / TC_EPI_GROUPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_CH = 8;          // accumulator columns scanned per epilogue step
-constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4 + TC_EPI_GROUPS * TC_CH * TC_BM * 4;   // slots + group maxima + scan buffers
+constexpr int TC_CH = 32;         // accumulator columns scanned per epilogue step
+constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4;   // slots + group maxima
 constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int RS_PMAX = 128;      // most candidates rescored per row
@@ -98,6 +98,31 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// v[i] for a run-time i in [0,32): a five-level select tree (31 SEL), registers cannot be indexed
+__device__ __forceinline__ float pick32(const float (&v)[32], int i) {
+    float a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (i & 16) ? v[j + 16] : v[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (i & 8) ? a[j + 8] : a[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = (i & 4) ? b[j + 4] : b[j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) d[j] = (i & 2) ? c[j + 2] : c[j];
+    return (i & 1) ? d[1] : d[0];
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -263,7 +288,6 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     float *list_sc = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
     int32_t *list_id = reinterpret_cast<int32_t *>(list_sc + TC_KP * TC_BM);
     float *list_gmax = reinterpret_cast<float *>(list_id + TC_KP * TC_BM);
-    float *scan_buf = list_gmax + (TC_KP / 8) * TC_BM;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES);
     uint64_t *full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
     uint64_t *empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
@@ -355,7 +379,6 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         float *sc = list_sc + grp * TC_KPG * TC_BM + row;
         int32_t *id = list_id + grp * TC_KPG * TC_BM + row;
         float *gmax = list_gmax + grp * TC_GROUPS * TC_BM + row;
-        float *sq = scan_buf + grp * TC_CH * TC_BM + row;
         for (int s = 0; s < TC_KPG; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
         for (int g = 0; g < TC_GROUPS; ++g) gmax[g * TC_BM] = F_INF;
         float tau = F_INF;
@@ -370,27 +393,28 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 #pragma unroll 1
             for (int c = 0; c < COLS / TC_CH; ++c) {
                 uint32_t v[TC_CH];
-                tmem_ld_32x8(taddr + c * TC_CH, v);
+                tmem_ld_32x32(taddr + c * TC_CH, v);
                 float4 yn[TC_CH / 4];
                 const float4 *yp = reinterpret_cast<const float4 *>(p.ynorm + n0 + c * TC_CH);
 #pragma unroll
                 for (int i = 0; i < TC_CH / 4; ++i) yn[i] = __ldg(yp + i);
                 tmem_ld_wait();
-                // branch-free scan: scores to the scan buffer, hits to a bit mask
+                // branch-free scan: scores stay in registers, hits go to a bit mask
+                float sv[TC_CH];
                 uint32_t mask = 0;
 #pragma unroll
                 for (int i = 0; i < TC_CH; ++i) {
                     const float y = (i & 3) == 0 ? yn[i >> 2].x : (i & 3) == 1 ? yn[i >> 2].y : (i & 3) == 2 ? yn[i >> 2].z : yn[i >> 2].w;
-                    const float s = fmaf(-2.0f, __uint_as_float(v[i]), y);
-                    sq[i * TC_BM] = s;
-                    mask |= (s < tau) ? (1u << i) : 0u;
+                    sv[i] = fmaf(-2.0f, __uint_as_float(v[i]), y);
+                    mask |= (sv[i] < tau) ? (1u << i) : 0u;
                 }
-                // drain: each lane inserts its own hits (rare after the first tiles)
+                // drain: each lane inserts its own hits (rare after the first tiles); the score of a hit is
+                // fetched from the register array with a select tree
                 while (__any_sync(0xffffffffu, mask != 0u)) {
+                    const int i = mask ? __ffs(mask) - 1 : 0;
+                    const float s = pick32(sv, i);
                     if (mask) {
-                        const int i = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const float s = sq[i * TC_BM];
                         if (s < tau) list_replace_max(sc, id, gmax, s, n0 + c * TC_CH + i, tau, gstar);
                     }
                 }
