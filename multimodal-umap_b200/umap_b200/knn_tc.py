@@ -57,11 +57,11 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
         gid = (rows + query_base).to(torch.int32)
         _, _, pst, _ = _call(query.index_select(0, rows), db, k, exclude_self, 0, gid, False, min_splits)
         if pst[0] > 0.1 * rows.numel():
-            min_splits, precision = DEEP_SPLITS, 1
+            precision = 1          # split operands shrink the error bound ~2000x: the shallow pool suffices again
     idx, dist, st, fallback = _call(query, db, k, exclude_self, query_base, None, same, min_splits, precision)
     n_fb = n_first = int(st[0])
     rescored, certified = st[1], st[2]
-    if n_fb and precision == 0:
+    if n_fb and not (precision == 1 and min_splits >= DEEP_SPLITS):
         # second level: only the uncertified rows, database in 8 splits (512 candidates per row), split operands
         rows = fallback[:n_fb].long()
         gid = (rows + query_base).to(torch.int32)
