@@ -33,8 +33,8 @@ constexpr int TC_BM = 128;        // query rows per CTA (= TMEM lanes)
 constexpr int TC_BN = 256;        // db rows per tile (= UMMA N, TMEM columns per accumulator)
 constexpr int TC_BK = 64;         // fp16 elements per k-block: 128 bytes = one swizzle span
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
-constexpr int TC_EPI_GROUPS = 2;  // epilogue warps per TMEM lane quarter; group g scans columns [128g, 128g+128) of a tile
+constexpr int TC_EPI_GROUPS = 4;  // epilogue warps per TMEM lane quarter; group g scans a 256/GROUPS-column slice of a tile
+constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. epilogue
 constexpr int TC_KP = 64;         // candidates kept per row and db split (TC_EPI_GROUPS lists of TC_KPG)
 constexpr int TC_KPG = TC_KP / TC_EPI_GROUPS;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
