@@ -75,6 +75,49 @@ spmm_csr_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
 }
 
+// m == 32 (the spectral solver's block width): 8 lanes per row, each lane owning 4 consecutive
+// columns (16-byte loads, one 128-byte segment per edge and row group), 4 rows per warp and two edges
+// per step in flight -- four times the memory-level parallelism of the warp-per-row form.
+__global__ void __launch_bounds__(256)
+spmm_csr_m32_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                    const float *__restrict__ val, int64_t n, const float *__restrict__ x,
+                    float alpha, float beta, const float *__restrict__ z, float gamma, float *__restrict__ y) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4 + grp;
+    const bool live = r < n;
+    const int64_t e0 = live ? rowptr[r] : 0, e1 = live ? rowptr[r + 1] : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // all four groups of a warp iterate together (shuffles): trip count = the longest row of the warp
+    int64_t len = e1 - e0;
+    for (int o = 8; o < 32; o <<= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    for (int64_t eb = 0; eb < len; eb += 8) {
+        const int64_t e = e0 + eb + sub;
+        const int32_t cj = (e < e1) ? col[e] : 0;
+        const float vj = (e < e1) ? val[e] : 0.f;           // padding edges contribute 0 * x[0]
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const int32_t ca = __shfl_sync(0xffffffffu, cj, j, 8), cb = __shfl_sync(0xffffffffu, cj, j + 1, 8);
+            const float va = __shfl_sync(0xffffffffu, vj, j, 8), vb = __shfl_sync(0xffffffffu, vj, j + 1, 8);
+            const float4 xa = *reinterpret_cast<const float4 *>(x + (int64_t)ca * 32 + sub * 4);
+            const float4 xb = *reinterpret_cast<const float4 *>(x + (int64_t)cb * 32 + sub * 4);
+            acc.x = fmaf(va, xa.x, acc.x); acc.y = fmaf(va, xa.y, acc.y); acc.z = fmaf(va, xa.z, acc.z); acc.w = fmaf(va, xa.w, acc.w);
+            acc.x = fmaf(vb, xb.x, acc.x); acc.y = fmaf(vb, xb.y, acc.y); acc.z = fmaf(vb, xb.z, acc.z); acc.w = fmaf(vb, xb.w, acc.w);
+        }
+    }
+    if (!live) return;
+    float4 out = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+    const int64_t o = r * 32 + sub * 4;
+    if (beta != 0.f) {
+        const float4 xv = *reinterpret_cast<const float4 *>(x + o);
+        out.x = fmaf(beta, xv.x, out.x); out.y = fmaf(beta, xv.y, out.y); out.z = fmaf(beta, xv.z, out.z); out.w = fmaf(beta, xv.w, out.w);
+    }
+    if (z) {
+        const float4 zv = *reinterpret_cast<const float4 *>(z + o);
+        out.x = fmaf(gamma, zv.x, out.x); out.y = fmaf(gamma, zv.y, out.y); out.z = fmaf(gamma, zv.z, out.z); out.w = fmaf(gamma, zv.w, out.w);
+    }
+    *reinterpret_cast<float4 *>(y + o) = out;
+}
+
 }  // namespace mmu
 
 extern "C" int mmu_embed_query(const int32_t *col, const float *w, int64_t n_rows, int k, const float *ref,
@@ -110,6 +153,14 @@ extern "C" int mmu_spmm_csr_axpby(const int64_t *rowptr, const int32_t *col, con
     MMU_CHECK_ARG(m >= 1, "mmu_spmm_csr_axpby: bad m");
     MMU_CHECK_ARG(x != y, "mmu_spmm_csr_axpby: x and y must not alias");
     if (n == 0) return MMU_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
+    if (m == 32 && aligned) {
+        const int64_t warps = (n + 3) / 4;
+        spmm_csr_m32_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, alpha,
+                                                                                                 beta, z, gamma, y);
+        MMU_LAUNCH_CHECK();
+        return MMU_OK;
+    }
     spmm_csr_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(rowptr, col, val, n, x, m, alpha,
                                                                                      beta, z, gamma, y);
     MMU_LAUNCH_CHECK();

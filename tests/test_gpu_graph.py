@@ -229,3 +229,35 @@ def test_spmm_csr():
     y = G.spmm(g, _cuda(x))
     ref = (a.astype(np.float64) @ x.astype(np.float64))
     assert np.allclose(y.cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("m", [32, 17])
+def test_spmm_axpby_all_forms(m):
+    """y = alpha A x + beta x + gamma z for the 32-column kernel (4 rows per warp) and the generic one:
+    ragged rows, empty rows, n not a multiple of 4, z aliasing the output (the Chebyshev recurrence)."""
+    import scipy.sparse as sp
+    from umap_b200 import graph as G
+    rng = np.random.default_rng(m)
+    n = 2999
+    a = sp.random(n, n, density=0.006, format="lil", dtype=np.float32, random_state=m)
+    a[5, :] = 0
+    a[n - 1, :] = 0
+    a[17, :60] = 1.0                                   # a long row
+    a = a.tocsr()
+    a.eliminate_zeros()
+    a.sort_indices()
+    coo = a.tocoo()
+    t = torch.sparse_coo_tensor(torch.from_numpy(np.stack([coo.row, coo.col]).astype(np.int64)),
+                                torch.from_numpy(coo.data), (n, n)).coalesce()
+    g = G.Graph.from_sparse_coo(t)
+    x = rng.standard_normal((n, m)).astype(np.float32)
+    z = rng.standard_normal((n, m)).astype(np.float32)
+    ax = a.astype(np.float64) @ x.astype(np.float64)
+    xt, zt = _cuda(x), _cuda(z)
+    y = G.spmm_axpby(g, g.val, xt, 1.0, 0.0, None, 0.0)
+    assert np.allclose(y.cpu().numpy(), ax, rtol=1e-4, atol=1e-5)
+    y = G.spmm_axpby(g, g.val, xt, 0.7, -1.3, None, 0.0)
+    assert np.allclose(y.cpu().numpy(), 0.7 * ax - 1.3 * x, rtol=1e-4, atol=1e-5)
+    out = zt.clone()
+    G.spmm_axpby(g, g.val, xt, 2.0, 0.5, out, -1.0, out=out)       # z aliases the output
+    assert np.allclose(out.cpu().numpy(), 2.0 * ax + 0.5 * x - z, rtol=1e-4, atol=1e-5)
