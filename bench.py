@@ -86,51 +86,96 @@ def make_data(workload: dict, seed: int = 0) -> dict:
 
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  Uses NVML in a background thread
+    (a polling nvidia-smi process takes driver locks for milliseconds per query and measurably slows the
+    host-latency-bound stages it is supposed to observe); falls back to nvidia-smi without pynvml."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int = 0):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
-        self.gpu_index = gpu_index
+    def __init__(self, gpu_index: int = 0, period_s: float = 0.1):
+        self.gpu_index, self.period = gpu_index, period_s
+        self.samples = []          # (sm_mhz, max_mhz, power_w, reasons_bitmask)
+        self.thread = self.proc = self.path = None
+        self.stop_flag = False
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(sm), float(mx), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.gpu_index]) if visible and visible.split(",")[0].isdigit() else self.gpu_index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "500",
                  "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                f = [t.strip() for t in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, f[5:9]):
-                    if val.lower().startswith("active"):
+        sm, mx, power, reasons = [], [], [], set()
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self._nv
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            for s_, m_, p_, r_ in self.samples:
+                sm.append(s_); mx.append(m_); power.append(p_)
+                for nm in names:
+                    if r_ & bits[nm]:
                         reasons.add(nm)
-            os.unlink(self.path)
-        except OSError:
-            pass
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            try:
+                for line in open(self.path):
+                    f = [t.strip() for t in line.split(",")]
+                    if len(f) < 9:
+                        continue
+                    try:
+                        sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                    except ValueError:
+                        continue
+                    for nm, val in zip(names, f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+                os.unlink(self.path)
+            except OSError:
+                pass
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler available"]}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        busy = [s_ for s_, p_ in zip(sm, power) if p_ > 0.5 * max(power)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "power_w_max": max(power), "samples": len(sm)}
 

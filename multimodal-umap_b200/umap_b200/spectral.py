@@ -68,6 +68,11 @@ def spectral_chebfsi(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 
     batched-GEMM Gram matrices, 32x32 dense eigenproblems.  Stops when every wanted Ritz pair has
     |A x - theta x| < tol (torch.lobpcg's default tolerance is sqrt(eps_fp32) = 3.5e-4).  Same
     output contract as embed_all: unit-norm columns, first (trivial) vector dropped, unscaled."""
+    debug = os.environ.get("MMUMAP_SPECTRAL_DEBUG") == "1"
+    if debug:
+        import time
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
     n, dev = g.n_rows, g.val.device
     m = out_dim + 1
     b = 32 if m <= 24 else -(-(m + 8) // 4) * 4
@@ -114,7 +119,11 @@ def spectral_chebfsi(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 
         y1 = y1 / y1.norm(dim=0, keepdim=True).clamp(min=1e-30)
         x = _orthonormalise(_orthonormalise(y1))
     vecs = x[:n, 1:m]
-    return (vecs / vecs.norm(dim=0, keepdim=True)).contiguous()
+    out = (vecs / vecs.norm(dim=0, keepdim=True)).contiguous()
+    if debug:
+        torch.cuda.synchronize()
+        print(f"  chebfsi n={n}: {it + 1} iterations, {(time.perf_counter() - t_start) * 1e3:.1f} ms wall")
+    return out
 
 
 def spectral_init(g: Graph, out_dim: int, method: str | None = None) -> torch.Tensor:
