@@ -411,8 +411,8 @@ def run_b200(args, workload, data):
     roof_sgd = {"kernel": "edge_forces_rb_kernel<4,4,8,fast>", "bound": "hbm", "achieved": forces_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": forces_gbs / hbm_peak if hbm_peak else None,
                 "traffic": 58.6e6, "traffic_note": "dram read+write per texts launch from profiles/r01_edge_forces_rb_ncu_full.txt: "
-                "the tables are L2 resident, DRAM traffic is 10x below the algorithmic bytes; the kernel is bound by L2 "
-                "random-access / red throughput (lts 56 %, l1tex 72 %)",
+                "the tables are L2 resident, DRAM traffic is 10x below the algorithmic bytes; the kernel is bound by the "
+                "per-SM L1->L2 path of the scattered vector reds (final ncu: L1/TEX 86.7 %, L2 59.7 %)",
                 "peak_source": peak_src, "share_of_step": forces["ms"] / total_ms if total_ms else None,
                 "ms_per_launch": forces["ms"] / max(forces["calls"], 1),
                 "edge_updates_per_s": forces["edge_updates"] / (forces["ms"] * 1e-3) if forces["ms"] > 0 else None}
