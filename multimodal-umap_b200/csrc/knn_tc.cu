@@ -44,6 +44,20 @@ constexpr int TC_CH = 32;         // accumulator columns scanned per epilogue st
 constexpr int TC_LIST_BYTES = TC_KP * TC_BM * 8 + (TC_KP / 8) * TC_BM * 4;   // slots + group maxima
 constexpr int TC_SMEM_BYTES = 1024 + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES + 256;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget");
+// NCTA = 2: a CTA pair (one TPC) runs ONE tcgen05.mma.cta_group::2 of M = 256 per step.  Each CTA stages its own
+// 128 query rows and HALF of the database tile (128 of the 256 rows), so the operand bytes an SM moves through
+// its shared memory per MMA drop from 24 KB (12 KB TMA fill + 12 KB operand read) to 16 KB -- at cta_group::1
+// that traffic, not the tensor pipe, is what bounds the kernel (ncu: tensor pipe 68 % = 128/192 B/clk).
+template <int NCTA>
+struct TcCfg {
+    static constexpr int B_ROWS = TC_BN / NCTA;
+    static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int STAGES = NCTA == 2 ? 4 : TC_STAGES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + TC_LIST_BYTES + 256;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area");
+};
 constexpr int RS_PMAX = 128;      // most candidates rescored per row
 #define F_INF __int_as_float(0x7f800000)
 
@@ -76,6 +90,46 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// both CTAs of a pair load into their own shared memory; the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -132,7 +186,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16: D fp32 (bits 4-5 = 1), A/B fp16 (format 0), both K-major, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// (the instruction descriptor is built where the MMAs are issued: M = 128 per CTA, 256 for a CTA pair)
 
 // ------------------------------------------------------------------ prep
 // column sums (deterministic two-level reduction) and the largest |x|
@@ -273,35 +327,46 @@ struct TcParams {
     int tiles_per_split;
     int n_splits;
     int split_major;         // grid = (n_splits, n_qblocks): co-resident CTAs share query blocks instead of db tiles
+    int n_qblocks;           // real query blocks (a pair launch rounds the grid up to an even number)
     int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
     float *cand_score;       // same layout
     float *tau;              // [n_qblocks][n_splits][TC_EPI_GROUPS][128]
 };
 
+// NCTA = 1: one CTA per query block.  NCTA = 2: clusters of two CTAs along the query-block axis of the grid; the pair
+// shares every database tile (rank r stages rows [128 r, 128 r + 128) of it) and the even-rank CTA issues the MMAs
+// for both.  tm_db's box is TC_BN / NCTA rows.
+template <int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                          const TcParams p) {
+    using Cfg = TcCfg<NCTA>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     // 1024-byte alignment (128-byte swizzle atoms) comes from the declaration, so that every pointer
     // below keeps its shared-memory provenance and compiles to LDS/STS
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *stage_base = smem;
-    float *list_sc = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
     int32_t *list_id = reinterpret_cast<int32_t *>(list_sc + TC_KP * TC_BM);
     float *list_gmax = reinterpret_cast<float *>(list_id + TC_KP * TC_BM);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES + TC_LIST_BYTES);
-    uint64_t *full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
-    uint64_t *empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
-    uint64_t *acc_full = bars + 2 * TC_STAGES;       // [2]          MMA -> epilogue
-    uint64_t *acc_empty = bars + 2 * TC_STAGES + 2;  // [2]          epilogue -> MMA
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + TC_LIST_BYTES);
+    uint64_t *full_bar = bars;                    // [STAGES]  TMA -> MMA        (pair: the leader's counts both CTAs' bytes)
+    uint64_t *empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA        (pair: commit multicast to both CTAs)
+    uint64_t *acc_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue   (pair: commit multicast to both CTAs)
+    uint64_t *acc_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA   (pair: both CTAs' warps arrive on the leader's)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // rasterisation: x is the fast index of the block scheduler.  Query-block-major (default) keeps ~148
     // different query blocks and ONE database region in flight -- right while 148 query tiles fit in L2
     // beside it; for long rows (148 x 128 x D x 2 B of query tiles alone overflow the L2) split-major keeps
     // few query blocks and all database regions in flight instead.
-    const int qblock = p.split_major ? blockIdx.y : blockIdx.x;
-    const int split = p.split_major ? blockIdx.x : blockIdx.y;
+    // A pair is always two x-neighbours of the grid: split-major pair launches use grid = (2 n_splits, n_qblocks / 2)
+    // with x = 2 split + rank.
+    const int qblock = !p.split_major ? blockIdx.x : NCTA == 2 ? 2 * blockIdx.y + (blockIdx.x & 1) : blockIdx.y;
+    const int split = !p.split_major ? blockIdx.y : NCTA == 2 ? (blockIdx.x >> 1) : blockIdx.x;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
@@ -312,17 +377,24 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_db)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * TC_EPI_GROUPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], NCTA * 4 * TC_EPI_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(2 * TC_BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {      // the same warp of both CTAs allocates the same columns in both SMs
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * TC_BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(2 * TC_BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();    // the peer's barriers are initialised before anything is signalled across
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -334,18 +406,29 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             for (int t = t0; t < t1; ++t) {
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t *a_dst = stage_base + stage * TC_STAGE_BYTES;
+                    uint8_t *a_dst = stage_base + stage * STAGE_BYTES;
                     uint8_t *b_dst = a_dst + TC_A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                    tma_load_2d(a_dst, &tm_q, &full_bar[stage], kb * TC_BK, qblock * TC_BM);
-                    tma_load_2d(b_dst, &tm_db, &full_bar[stage], kb * TC_BK, t * TC_BN);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (NCTA == 2) {
+                        // the leader expects the bytes of both CTAs; the peer's bytes may land first (the
+                        // transaction count goes negative for a moment, the phase cannot complete before the
+                        // leader's arrive)
+                        const uint32_t leader_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(a_dst, &tm_q, leader_bar, kb * TC_BK, qblock * TC_BM);
+                        tma_load_2d_pair(b_dst, &tm_db, leader_bar, kb * TC_BK, t * TC_BN + (int)cta_rank * Cfg::B_ROWS);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(a_dst, &tm_q, &full_bar[stage], kb * TC_BK, qblock * TC_BM);
+                        tma_load_2d(b_dst, &tm_db, &full_bar[stage], kb * TC_BK, t * TC_BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((NCTA * TC_BM) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < n_my_tiles; ++it) {
@@ -356,15 +439,20 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + stage * TC_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(stage_base + stage * STAGE_BYTES);
                     const uint64_t adesc = umma_smem_desc(a_addr);
                     const uint64_t bdesc = umma_smem_desc(a_addr + TC_A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)      // +32 bytes (2 x 16 B) per UMMA_K = 16 halfs
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
-                    if (kb == p.n_kblocks - 1) umma_commit(&acc_full[acc]);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < TC_BK / 16; ++k) {    // +32 bytes (2 x 16 B) per UMMA_K = 16 halfs
+                        if (NCTA == 2) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                        else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if (NCTA == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    if (kb == p.n_kblocks - 1) {
+                        if (NCTA == 2) umma_commit_pair(&acc_full[acc]); else umma_commit(&acc_full[acc]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -421,22 +509,31 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (lane == 0) {
+                if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acc]), 0));
+                else mbar_arrive(&acc_empty[acc]);
+            }
         }
         // flush: [qblock][split][slot][row] keeps the stores coalesced
-        const int64_t base = (((int64_t)qblock * p.n_splits + split) * TC_KP + grp * TC_KPG) * TC_BM;
-        for (int s = 0; s < TC_KPG; ++s) {
-            p.cand_idx[base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
-            p.cand_score[base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
+        if (qblock < p.n_qblocks) {                    // the odd block out of a pair launch computes padding only
+            const int64_t base = (((int64_t)qblock * p.n_splits + split) * TC_KP + grp * TC_KPG) * TC_BM;
+            for (int s = 0; s < TC_KPG; ++s) {
+                p.cand_idx[base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
+                p.cand_score[base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
+            }
+            p.tau[(((int64_t)qblock * p.n_splits + split) * TC_EPI_GROUPS + grp) * TC_BM + row] = tau;
         }
-        p.tau[(((int64_t)qblock * p.n_splits + split) * TC_EPI_GROUPS + grp) * TC_BM + row] = tau;
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();    // neither CTA leaves (or frees TMEM) while the other still reads its memory
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
     }
 }
 
@@ -720,7 +817,7 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     L.dim_pad = (int)round_up(dim, TC_BK);
     L.width = split ? 3 * L.dim_pad : L.dim_pad;
     L.n_pad = round_up(n_db, TC_BN);                 // also a multiple of TC_BM
-    L.q_pad = shared_operand ? L.n_pad : round_up(n_query, TC_BM);
+    L.q_pad = shared_operand ? L.n_pad : round_up(n_query, 2 * TC_BM);   // whole CTA pairs
     L.n_qblocks = (int)(round_up(n_query, TC_BM) / TC_BM);
     L.n_tiles = (int)(L.n_pad / TC_BN);
     int sms = sm_count();
@@ -827,14 +924,25 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     MMU_LAUNCH_CHECK_N(launches);
 
     // ---- candidates
+    // CTA pairs (cta_group::2) whenever there are two query blocks to pair; MMUMAP_KNN_CTA_PAIRS=0 keeps one CTA
+    // per query block (A/B measurements)
+    static int pairs_allowed = -1;
+    if (pairs_allowed < 0) {
+        const char *e = getenv("MMUMAP_KNN_CTA_PAIRS");
+        pairs_allowed = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int ncta = (pairs_allowed && L.n_qblocks >= 2) ? 2 : 1;
     CUtensorMap tm_q, tm_db;
     int rc = make_map(&tm_q, q16, L.q_pad, L.width, TC_BM);
     if (rc) return rc;
-    rc = make_map(&tm_db, db16, L.n_pad, L.width, TC_BN);
+    rc = make_map(&tm_db, db16, L.n_pad, L.width, TC_BN / ncta);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<1>::SMEM_BYTES));
+        MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<2>::SMEM_BYTES));
         attr_set = true;
     }
     TcParams tp;
@@ -843,6 +951,7 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     tp.n_tiles = L.n_tiles;
     tp.tiles_per_split = L.tiles_per_split;
     tp.n_splits = L.n_splits;
+    tp.n_qblocks = L.n_qblocks;
     tp.cand_idx = cidx;
     tp.cand_score = cscore;
     tp.tau = tau;
@@ -852,8 +961,25 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         const size_t q_tiles_in_flight = (size_t)sms * TC_BM * L.width * 2;
         tp.split_major = (L.n_splits > 1 && q_tiles_in_flight > ((size_t)48 << 20)) ? 1 : 0;
     }
-    const dim3 grid = tp.split_major ? dim3(L.n_splits, L.n_qblocks) : dim3(L.n_qblocks, L.n_splits);
-    knn_tc_candidates_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_q, tm_db, tp);
+    if (ncta == 2) {
+        const unsigned qb = (unsigned)((L.n_qblocks + 1) & ~1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = tp.split_major ? dim3(2 * L.n_splits, qb / 2) : dim3(qb, L.n_splits);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcCfg<2>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;    // two query blocks, x-neighbours in the grid
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MMU_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_candidates_kernel<2>, tm_q, tm_db, tp));
+    } else {
+        const dim3 grid = tp.split_major ? dim3(L.n_splits, L.n_qblocks) : dim3(L.n_qblocks, L.n_splits);
+        knn_tc_candidates_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, st>>>(tm_q, tm_db, tp);
+    }
     MMU_LAUNCH_CHECK();
 
     // ---- certify + rescore
