@@ -406,8 +406,8 @@ def run_b200(args, workload, data):
                 "achieved": knn_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": knn_tflops / tensor_peak,
                 "traffic": None, "peak_source": peak_src, "share_of_step": knn["ms"] / total_ms if total_ms else None,
                 "ms_per_launch": knn["ms"] / max(knn["calls"], 1),
-                "ncu": "profiles/r01_final_knn_tc_candidates_8warp_ncu_full.txt: tensor pipe active 68.6 % (texts, 30.5 ms) / "
-                       "78.5 % (images, 6.4 ms) of peak sustained active"}
+                "ncu": "profiles/r01_knn_tc_candidates_cta_pairs_ncu_full.txt (cta_group::2 pairs): tensor pipe active 78.2 % "
+                       "(texts, 28.2 ms) / 87.7 % (images, 6.05 ms) of peak sustained active at SM clocks of 1.48 / 1.33 GHz"}
     roof_sgd = {"kernel": "edge_forces_rb_kernel<4,4,8,fast>", "bound": "hbm", "achieved": forces_gbs, "peak": hbm_peak,
                 "unit": "GB/s", "frac": forces_gbs / hbm_peak if hbm_peak else None,
                 "traffic": 58.6e6, "traffic_note": "dram read+write per texts launch from profiles/r01_edge_forces_rb_ncu_full.txt: "

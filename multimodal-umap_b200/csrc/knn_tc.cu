@@ -328,6 +328,9 @@ struct TcParams {
     int n_splits;
     int split_major;         // grid = (n_splits, n_qblocks): co-resident CTAs share query blocks instead of db tiles
     int n_qblocks;           // real query blocks (a pair launch rounds the grid up to an even number)
+    int window_begin;        // this launch covers tiles [window_begin, window_begin + window_tiles) of every split
+    int window_tiles;
+    int resume;              // continue the lists an earlier window left in cand_idx / cand_score
     int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
     float *cand_score;       // same layout
     float *tau;              // [n_qblocks][n_splits][TC_EPI_GROUPS][128]
@@ -368,8 +371,8 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const int qblock = !p.split_major ? blockIdx.x : NCTA == 2 ? 2 * blockIdx.y + (blockIdx.x & 1) : blockIdx.y;
     const int split = !p.split_major ? blockIdx.y : NCTA == 2 ? (blockIdx.x >> 1) : blockIdx.x;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
-    const int t0 = split * p.tiles_per_split;
-    const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+    const int t0 = split * p.tiles_per_split + p.window_begin;
+    const int t1 = min(min(p.n_tiles, (split + 1) * p.tiles_per_split), t0 + p.window_tiles);
     const int n_my_tiles = max(0, t1 - t0);
 
     if (warp == 0 && lane == 0) {
@@ -467,10 +470,23 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         float *sc = list_sc + grp * TC_KPG * TC_BM + row;
         int32_t *id = list_id + grp * TC_KPG * TC_BM + row;
         float *gmax = list_gmax + grp * TC_GROUPS * TC_BM + row;
-        for (int s = 0; s < TC_KPG; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
-        for (int g = 0; g < TC_GROUPS; ++g) gmax[g * TC_BM] = F_INF;
-        float tau = F_INF;
+        const int64_t list_base = (((int64_t)qblock * p.n_splits + split) * TC_KP + grp * TC_KPG) * TC_BM;
+        if (p.resume && qblock < p.n_qblocks) {
+            for (int s = 0; s < TC_KPG; ++s) {
+                sc[s * TC_BM] = p.cand_score[list_base + (int64_t)s * TC_BM + row];
+                id[s * TC_BM] = p.cand_idx[list_base + (int64_t)s * TC_BM + row];
+            }
+        } else {
+            for (int s = 0; s < TC_KPG; ++s) { sc[s * TC_BM] = F_INF; id[s * TC_BM] = -1; }
+        }
+        float tau = -F_INF;
         int gstar = 0;
+        for (int g = 0; g < TC_GROUPS; ++g) {
+            float gm = sc[g * 8 * TC_BM];
+            for (int u = 1; u < 8; ++u) gm = fmaxf(gm, sc[(g * 8 + u) * TC_BM]);
+            gmax[g * TC_BM] = gm;
+            if (gm > tau) { tau = gm; gstar = g; }
+        }
         constexpr int COLS = TC_BN / TC_EPI_GROUPS;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int acc = it & 1;
@@ -516,10 +532,9 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         }
         // flush: [qblock][split][slot][row] keeps the stores coalesced
         if (qblock < p.n_qblocks) {                    // the odd block out of a pair launch computes padding only
-            const int64_t base = (((int64_t)qblock * p.n_splits + split) * TC_KP + grp * TC_KPG) * TC_BM;
             for (int s = 0; s < TC_KPG; ++s) {
-                p.cand_idx[base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
-                p.cand_score[base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
+                p.cand_idx[list_base + (int64_t)s * TC_BM + row] = id[s * TC_BM];
+                p.cand_score[list_base + (int64_t)s * TC_BM + row] = sc[s * TC_BM];
             }
             p.tau[(((int64_t)qblock * p.n_splits + split) * TC_EPI_GROUPS + grp) * TC_BM + row] = tau;
         }
@@ -924,14 +939,12 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     MMU_LAUNCH_CHECK_N(launches);
 
     // ---- candidates
-    // CTA pairs (cta_group::2) whenever there are two query blocks to pair; MMUMAP_KNN_CTA_PAIRS=0 keeps one CTA
-    // per query block (A/B measurements)
-    static int pairs_allowed = -1;
-    if (pairs_allowed < 0) {
-        const char *e = getenv("MMUMAP_KNN_CTA_PAIRS");
-        pairs_allowed = (e && e[0] == '0') ? 0 : 1;
-    }
-    const int ncta = (pairs_allowed && L.n_qblocks >= 2) ? 2 : 1;
+    // CTA pairs (cta_group::2) for long rows; MMUMAP_KNN_CTA_PAIRS=0 keeps one CTA per query block (A/B measurements)
+    const char *pe = getenv("MMUMAP_KNN_CTA_PAIRS");
+    const int pairs_allowed = (pe && pe[0] == '0') ? 0 : 1;
+    // Short rows (width < 512: at most 7 k-blocks per tile) are bound by the per-tile epilogue, not by operand
+    // traffic; there a pair only couples the two epilogues (1M x 128, k = 30: 795 ms paired, 695 ms unpaired).
+    const int ncta = (pairs_allowed && L.n_qblocks >= 2 && L.width >= 512) ? 2 : 1;
     CUtensorMap tm_q, tm_db;
     int rc = make_map(&tm_q, q16, L.q_pad, L.width, TC_BM);
     if (rc) return rc;
@@ -961,7 +974,25 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         const size_t q_tiles_in_flight = (size_t)sms * TC_BM * L.width * 2;
         tp.split_major = (L.n_splits > 1 && q_tiles_in_flight > ((size_t)48 << 20)) ? 1 : 0;
     }
+    tp.window_begin = 0;
+    tp.window_tiles = L.tiles_per_split;
+    tp.resume = 0;
     if (ncta == 2) {
+        // Pairs do not stay in lock-step over a long database pass the way single CTAs do (traced on 1M x 768: the
+        // spread of the CTAs' positions grows by ~0.2 ms per wave until every pair streams its tiles from DRAM,
+        // 3.9 TB instead of 82 GB).  So a database region that does not fit in L2 is walked in windows of ~48 MB,
+        // one launch per window over ALL query blocks; the lists carry over through cand_idx / cand_score.
+        const size_t tile_bytes = (size_t)TC_BN * L.width * 2;
+        const size_t region = (size_t)L.n_splits * L.tiles_per_split * tile_bytes;
+        // MMUMAP_KNN_WINDOW_MB: window size; set explicitly it applies to every pair launch (tests), 0 = one launch
+        const char *e = getenv("MMUMAP_KNN_WINDOW_MB");
+        const long window_mb = e ? atol(e) : 48;
+        // (split-major launches keep few query blocks and every split in flight; measured fine as one launch)
+        if (window_mb > 0 && (e || (region > ((size_t)160 << 20) && !tp.split_major))) {
+            size_t w = ((size_t)window_mb << 20) / ((size_t)L.n_splits * tile_bytes);
+            tp.window_tiles = (int)(w < 8 ? 8 : w);
+            if (tp.window_tiles > L.tiles_per_split) tp.window_tiles = L.tiles_per_split;
+        }
         const unsigned qb = (unsigned)((L.n_qblocks + 1) & ~1);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = tp.split_major ? dim3(2 * L.n_splits, qb / 2) : dim3(qb, L.n_splits);
@@ -975,7 +1006,12 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MMU_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_candidates_kernel<2>, tm_q, tm_db, tp));
+        for (int w0 = 0; w0 < L.tiles_per_split; w0 += tp.window_tiles) {
+            tp.window_begin = w0;
+            tp.resume = w0 > 0;
+            MMU_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_candidates_kernel<2>, tm_q, tm_db, tp));
+            if (w0 > 0) mmu_launch_count_add(1);
+        }
     } else {
         const dim3 grid = tp.split_major ? dim3(L.n_splits, L.n_qblocks) : dim3(L.n_qblocks, L.n_splits);
         knn_tc_candidates_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, st>>>(tm_q, tm_db, tp);

@@ -16,10 +16,12 @@ def main():
     shapes = [("texts", 158915, 768, "bert"), ("images", 31783, 4096, "vae")]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         shapes = [("texts", 40000, 768, "bert"), ("images", 12000, 4096, "vae")]
+    if len(sys.argv) > 1 and sys.argv[1] == "c3":
+        shapes = [("c3", 1000000, 768, "bert")]
     reps = int(os.environ.get("REPS", "3"))
     for name, n, d, kind in shapes:
         x = data(n, d, kind)
-        for _ in range(2):
+        for _ in range(int(os.environ.get("WARM", "2"))):
             G.knn_graph(x, x, 15, True, method="tc")
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -153,3 +153,34 @@ def test_deep_candidate_pool_certifies_what_one_list_cannot():
     _same(ti, td, si.cpu().numpy(), sd.cpu().numpy())
     assert st["first_pass_uncertified"] > 0.02 * n or st["precision"] == 1, st      # the fp16 pass alone is not enough here
     assert st["fallback_rows"] < 0.001 * n, st                                       # ... the split-fp16 deep pool is
+
+
+@pytest.mark.parametrize("n,d,kind", [(12000, 768, "bert"), (5000, 4096, "vae")])
+def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind, monkeypatch):
+    """The candidate kernel has two forms (knn_tc.cu: cta_group::2 CTA pairs for long rows, one CTA per
+    query block otherwise) and the pair form walks a large database in windows, carrying the per-row
+    lists from launch to launch.  All of them must give the exhaustive kernel's result bit for bit;
+    an odd number of query blocks (the last pair is half padding) is part of the case."""
+    from umap_b200 import graph as G
+    g = torch.Generator(device="cuda").manual_seed(n + 1)
+    cl = torch.arange(n, device="cuda") % 64
+    if kind == "bert":
+        x = torch.tanh(torch.randn((64, d), generator=g, device="cuda")[cl] + 0.5 * torch.randn((n, d), generator=g, device="cuda"))
+    else:
+        x = 2.0 * torch.randn((64, d), generator=g, device="cuda")[cl] + 4.0 * torch.randn((n, d), generator=g, device="cuda")
+    x = x.contiguous()
+    si, sd = G.knn_exact_simt(x, x, 15, True)
+    si, sd = si.cpu().numpy(), sd.cpu().numpy()
+    q = x[: 128 * 37 + 5].contiguous()                       # 38 query blocks in query mode, 37 full
+    qi, qd = G.knn_exact_simt(q, x, 15, False)
+    qi, qd = qi.cpu().numpy(), qd.cpu().numpy()
+    for env in ({"MMUMAP_KNN_WINDOW_MB": "1"}, {"MMUMAP_KNN_WINDOW_MB": "0"}, {"MMUMAP_KNN_CTA_PAIRS": "0"}):
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        ti, td, st = _tc(x, x, 15, True)
+        _same(ti, td, si, sd)
+        assert st["fallback_rows"] <= 0.02 * n, (env, st)
+        ti, td, st = _tc(q, x, 15, False)
+        _same(ti, td, qi, qd)
+        for key in env:
+            monkeypatch.delenv(key)
