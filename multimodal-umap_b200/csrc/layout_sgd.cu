@@ -283,6 +283,120 @@ __device__ __forceinline__ float pair_coef(float s_raw, bool attractive, float a
     }
 }
 
+// Run form of the kernel below: a group walks a CONTIGUOUS run of kept edges instead of a grid-stride set.  The
+// kept list is row sorted inside every sampler block's chunk, so consecutive edges mostly share their head row:
+// its gradient is accumulated in registers and leaves with ONE vector red per (run, row) instead of one per
+// edge, and the head row itself stays an L1 hit.  The kernel is bound by the L1->crossbar request port
+// (ncu: l1tex__m_l1tex2xbar_req_cycles_active 78-88 %), where every 64-byte red costs its payload cycles.
+template <int VEC, int LANES, int R, bool FAST>
+__global__ void __launch_bounds__(256, 3)
+edge_forces_runs_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                        const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+                        const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
+                        int batch_size, uint32_t rep_count, const float *__restrict__ head,
+                        const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
+                        float a, float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+    constexpr int DIM = VEC * LANES;
+    constexpr int NP = R + 1;
+    constexpr int NCALL = (R + 3) / 4;
+    constexpr int ROUNDS = (NP + LANES - 1) / LANES;
+    const int n_kept = *kept_count;
+    const uint32_t epoch = st->epoch;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int gl = threadIdx.x % LANES;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+    const float inv_nb = 1.0f / (float)n_batches;
+    const bool want_loss = loss_out != nullptr;
+    float loss_acc = 0.f;
+    const int per = (int)((n_kept + n_groups - 1) / n_groups);      // run length: the same for every group
+    const int64_t e_begin = gid * per;
+    int32_t cur_i = -1;
+    Vec<VEC> gi;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
+    for (int t = 0; t < per; ++t) {
+        const int64_t e = e_begin + t;
+        const bool active = e < n_kept;
+        int32_t p = 0, i = 0;
+        uint32_t t_idx[NP];
+        float sc_a = 0.f, sc_r = 0.f;
+        t_idx[0] = 0;
+        if (active) {
+            p = kept_pos[e];
+            i = row[p];
+            t_idx[0] = (uint32_t)col[p];
+            const float kb = (float)batch_kept[i / batch_size];
+            sc_a = inv_nb / kb;
+            sc_r = inv_nb / (kb * (float)R);
+            if (i != cur_i) {                                     // group-uniform: the lanes of a group share e
+                if (cur_i >= 0) red_vec<VEC>(grad_head + (int64_t)cur_i * DIM + gl * VEC, gi, 1.0f);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
+                cur_i = i;
+            }
+        }
+        if (neg) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) t_idx[r + 1] = active ? (uint32_t)neg[e * R + r] : 0u;
+        } else if (LANES >= NCALL) {
+            const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)(gl % NCALL), epoch, STREAM_NEG, k0, k1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t mine = (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w;
+                t_idx[r + 1] = urange(__shfl_sync(0xffffffffu, mine, r >> 2, LANES), rep_count);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCALL; ++c) {
+                const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)c, epoch, STREAM_NEG, k0, k1);
+                if (4 * c + 0 < R) t_idx[4 * c + 1] = urange(w.x, rep_count);
+                if (4 * c + 1 < R) t_idx[4 * c + 2] = urange(w.y, rep_count);
+                if (4 * c + 2 < R) t_idx[4 * c + 3] = urange(w.z, rep_count);
+                if (4 * c + 3 < R) t_idx[4 * c + 4] = urange(w.w, rep_count);
+            }
+        }
+        const Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * DIM + gl * VEC);
+        Vec<VEC> df[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) df[q] = load_vec<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
+        float s[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { df[q].v[c] = yi.v[c] - df[q].v[c]; acc = fmaf(df[q].v[c], df[q].v[c], acc); }
+            s[q] = group_sum<LANES>(acc);
+        }
+        float cv[ROUNDS];
+#pragma unroll
+        for (int u0 = 0; u0 < ROUNDS; ++u0) {
+            float sv = 1.0f;
+            bool valid = false;
+#pragma unroll
+            for (int u = 0; u < LANES; ++u)
+                if (u0 * LANES + u < NP && gl == u) { sv = s[u0 * LANES + u]; valid = true; }
+            float l = 0.f;
+            const float cf = pair_coef<FAST>(sv, u0 == 0 && gl == 0, a, b, sc_a, sc_r, want_loss, l);
+            cv[u0] = (valid && active) ? cf : 0.f;
+            if (want_loss && valid && active) loss_acc += l;
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const float coef = LANES == 1 ? cv[q] : __shfl_sync(0xffffffffu, cv[q / LANES], q % LANES, LANES);
+            Vec<VEC> g;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df[q].v[c]; gi.v[c] += g.v[c]; }
+            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)t_idx[q] * DIM + gl * VEC, g, -1.0f);
+        }
+    }
+    if (cur_i >= 0) red_vec<VEC>(grad_head + (int64_t)cur_i * DIM + gl * VEC, gi, 1.0f);
+    if (want_loss) {
+        loss_acc = warp_sum(loss_acc);
+        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
+    }
+}
+
 template <int VEC, int LANES, int R, bool FAST, bool REC>
 __global__ void __launch_bounds__(256, 3)
 edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
@@ -916,13 +1030,24 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
     cudaStream_t st = as_stream(stream);
     const OptState *os = reinterpret_cast<const OptState *>(state);
     unsigned blocks = persistent_blocks(256, 8);
+    // run form (head gradient accumulated per run of equal rows) unless MMUMAP_FORCE_RUNS=0
+    const char *runs_env = getenv("MMUMAP_FORCE_RUNS");
+    const bool runs = !(runs_env && runs_env[0] == '0');
 #define MMU_FORCES(V, L)                                                                                        \
     edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept, n_batches, \
                                                      batch_size, num_rep, (uint32_t)rep_count, head, tail,       \
                                                      grad_head, grad_tail, dim, a, b, seed, os, loss)
 #define MMU_FORCES_RB(V, L, RR)                                                                                  \
     do {                                                                                                         \
-        if (fast_math)                                                                                           \
+        if (runs && fast_math)                                                                                   \
+            edge_forces_runs_kernel<V, L, RR, true><<<blocks, 256, 0, st>>>(                                     \
+                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size,                          \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
+        else if (runs)                                                                                           \
+            edge_forces_runs_kernel<V, L, RR, false><<<blocks, 256, 0, st>>>(                                    \
+                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size,                          \
+                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
+        else if (fast_math)                                                                                      \
             edge_forces_rb_kernel<V, L, RR, true, false><<<blocks, 256, 0, st>>>(                                \
                 row, col, kept_pos, nullptr, kept_count, neg, batch_kept, n_batches, batch_size,                 \
                 (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
