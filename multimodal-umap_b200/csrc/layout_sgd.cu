@@ -1033,6 +1033,10 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
     // run form (head gradient accumulated per run of equal rows) unless MMUMAP_FORCE_RUNS=0
     const char *runs_env = getenv("MMUMAP_FORCE_RUNS");
     const bool runs = !(runs_env && runs_env[0] == '0');
+    // the register-blocked kernels hold 3 blocks per SM (__launch_bounds__(256, 3)): a grid of whole waves
+    // (measured per epoch on C2: 3/SM 279.9 us, 6/SM 284.3, 8/SM 289.4, 9/SM 279.9, 12/SM 291.1)
+    const unsigned blocks_generic = blocks;
+    if (num_rep == 8 || num_rep == 4) blocks = persistent_blocks(256, 3);
 #define MMU_FORCES(V, L)                                                                                        \
     edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept, n_batches, \
                                                      batch_size, num_rep, (uint32_t)rep_count, head, tail,       \
@@ -1071,7 +1075,7 @@ extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int
         case 64: MMU_FORCES_DIM(4, 16); break;
         case 128: MMU_FORCES_DIM(4, 32); break;
         default:
-            edge_forces_generic_kernel<<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept,
+            edge_forces_generic_kernel<<<blocks_generic, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept,
                                                                n_batches, batch_size, num_rep, (uint32_t)rep_count,
                                                                head, tail, grad_head, grad_tail, dim, a, b, seed, os, loss);
     }
@@ -1101,7 +1105,7 @@ extern "C" int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *k
     cudaStream_t st = as_stream(stream);
     const OptState *os = reinterpret_cast<const OptState *>(state);
     const int4 *rec = reinterpret_cast<const int4 *>(kept_rec);
-    unsigned blocks = persistent_blocks(256, 8);
+    unsigned blocks = persistent_blocks(256, 3);      // whole waves at 3 blocks per SM
 #define MMU_FREC(V, L, RR)                                                                                       \
     do {                                                                                                         \
         if (fast_math)                                                                                           \

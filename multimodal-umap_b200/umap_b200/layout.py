@@ -236,9 +236,14 @@ class LayoutOptimizer:
 
     def _epoch_tail(self):
         """InfoNCE, gradient all-reduce, Adam: everything of an epoch after the force kernels."""
+        self._infonce_all(stream())
+        self._adam_tail()
+
+    def _infonce_all(self, st):
+        """Cross-modal InfoNCE gradients of one epoch, launched on stream `st` (model.py:459-472)."""
         host = self.sample_stream == "host"
         dev = torch.device("cuda")
-        if self.mode == "fit":                                           # model.py:459-472
+        if self.mode == "fit":
             n = len(self.mods)
             sid = 0
             for i in range(n):
@@ -258,8 +263,10 @@ class LayoutOptimizer:
                         check(lib().mmu_infonce_bidir(ptr(src.p), ptr(dst.p), num, a_lo, a_hi, src.dim, ptr(pf), ptr(nf),
                                                       ptr(pr), ptr(nr), INFONCE_NEG, INFONCE_CHUNK, self.alpha, INFONCE_TAU,
                                                       ptr(src.g), ptr(dst.g), self.seed, sid, ptr(self.state),
-                                                      ptr(self.loss), stream()), "mmu_infonce_bidir")
+                                                      ptr(self.loss), st), "mmu_infonce_bidir")
                     sid += 2
+
+    def _adam_tail(self):
         # multi-GPU: one all-reduce of the flat gradient buffer, then the identical Adam step everywhere
         D.all_reduce_sum(self.flat[1])
         check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
@@ -288,6 +295,11 @@ class LayoutOptimizer:
         sampled = [None, None]
         consumed = [None, None]
         base = self.done
+        # The InfoNCE kernel (latency bound, 2 blocks per SM) reads the same embedding state as the force kernels
+        # (L1->crossbar bound) and only adds to the gradient buffer, so it runs beside them on the second stream:
+        # after the previous epoch's Adam step, before this epoch's.
+        side_nce = self.mode == "fit" and len(self.mods) > 1 and os.environ.get("MMUMAP_NCE_OVERLAP", "1") == "1"
+        stepped = None
 
         def issue_sample(e):
             b = e & 1
@@ -306,9 +318,17 @@ class LayoutOptimizer:
 
         issue_sample(0)
         for e in range(epochs):
+            b = e & 1
+            nce_done = None
+            if side_nce:
+                with torch.cuda.stream(side):
+                    if stepped is not None:
+                        side.wait_event(stepped)
+                    self._infonce_all(side.cuda_stream)
+                    nce_done = torch.cuda.Event()
+                    nce_done.record(side)
             if e + 1 < epochs:
                 issue_sample(e + 1)
-            b = e & 1
             main.wait_event(sampled[b])
             for mi, mod in enumerate(self.mods):
                 kp, kc, bk = bufs[mi][b]
@@ -317,7 +337,14 @@ class LayoutOptimizer:
             ev = torch.cuda.Event()
             ev.record(main)
             consumed[b] = ev
-            self._epoch_tail()
+            if side_nce:
+                main.wait_event(nce_done)
+            else:
+                self._infonce_all(stream())
+            self._adam_tail()
+            if side_nce:
+                stepped = torch.cuda.Event()
+                stepped.record(main)
         main.wait_stream(side)
 
     def run(self, epochs: int):
