@@ -149,6 +149,12 @@ int mmu_embed_query(const int32_t *col, const float *w, int64_t n_rows, int k, c
 int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,
                  const float *x, int m, float *y, mmu_stream_t stream);
 
+/* Eigendecomposition of ONE small symmetric matrix (n <= 64, row-major; (a + a^T)/2 is used) by parallel
+ * cyclic Jacobi in a single CTA: lam[n] ascending, v[n x n] row-major with eigenvector j in column j
+ * (torch.linalg.eigh's convention).  The dense Rayleigh-Ritz / orthonormalisation steps of the spectral
+ * initialisation without a host round trip.  ref: model.py:232 (inside torch.lobpcg) */
+int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_stream_t stream);
+
 /* y = alpha * (A x) + beta * x + gamma * z  (z nullable; z may alias y): one three-term
  * Chebyshev recurrence step of the spectral initialisation per launch.  ref: model.py:221-234 */
 int mmu_spmm_csr_axpby(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n,

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "mmu_spmm_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_spmm_csr_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float, c_void_p,
                                    c_float, c_void_p, c_void_p]),
+    "mmu_eigh_small": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
     "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
     "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,

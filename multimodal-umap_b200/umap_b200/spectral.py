@@ -15,6 +15,7 @@ import os
 import torch
 
 from .graph import Graph, spmm, spmm_axpby
+from .native import check, lib, ptr, stream
 
 
 def normalized_adjacency(g: Graph) -> torch.Tensor:
@@ -44,11 +45,23 @@ def _gram(x: torch.Tensor, y: torch.Tensor, chunk: int = 256) -> torch.Tensor:
     return torch.bmm(x.view(c, chunk, x.shape[1]).transpose(1, 2), y.view(c, chunk, y.shape[1])).sum(0)
 
 
+EIGH_DEVICE_MAX = 64
+
+
 def _eigh_small(a: torch.Tensor):
-    """Symmetric eigendecomposition of a b x b (b ~ 32) matrix: LAPACK on the host is ~4x faster than
-    cuSOLVER's syevd launch sequence at this size, including both copies."""
-    lam, v = torch.linalg.eigh(a.cpu())
-    return lam.to(a.device), v.to(a.device)
+    """Symmetric eigendecomposition of a b x b (b ~ 32) matrix, eigenvalues ascending: the engine's
+    one-CTA Jacobi kernel (mmu_eigh_small) -- no host round trip, no stream synchronisation; cuSOLVER's
+    syevd launch sequence is ~4x slower than even a LAPACK round trip at this size.  Blocks wider than
+    the kernel's limit (out_dim > 55) go through LAPACK on the host."""
+    n = a.shape[0]
+    if n > EIGH_DEVICE_MAX or os.environ.get("MMUMAP_EIGH") == "host":
+        lam, v = torch.linalg.eigh(a.cpu())
+        return lam.to(a.device), v.to(a.device)
+    a = a.contiguous()
+    lam = torch.empty(n, dtype=torch.float32, device=a.device)
+    v = torch.empty((n, n), dtype=torch.float32, device=a.device)
+    check(lib().mmu_eigh_small(ptr(a), n, ptr(lam), ptr(v), stream()), "mmu_eigh_small")
+    return lam, v
 
 
 def _orthonormalise(x: torch.Tensor) -> torch.Tensor:

@@ -48,3 +48,27 @@ def test_spectral_init_solves_the_reference_operator(method, n, out_dim, centers
     upto = int(np.searchsorted(ew, ew[out_dim] + 5e-3, side="right"))
     proj = ev[:, :upto].T @ v
     assert np.all(np.linalg.norm(proj, axis=0) > 0.98)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 17, 32, 48, 64])
+def test_eigh_small_matches_lapack(n):
+    """mmu_eigh_small (one-CTA Jacobi) against float64 LAPACK: eigenvalues, orthonormality,
+    reconstruction; a Gram matrix with a wide spectrum (what SVQB hands it) and an indefinite
+    Rayleigh-Ritz matrix."""
+    from umap_b200.spectral import _eigh_small
+    rng = np.random.default_rng(n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    mats = [q @ np.diag(np.logspace(0, -7, n)) @ q.T, q @ np.diag(np.linspace(-0.8, 1.0, n)) @ q.T,
+            np.eye(n), np.zeros((n, n))]
+    for a in mats:
+        a = 0.5 * (a + a.T)
+        lam, v = _eigh_small(torch.from_numpy(a.astype(np.float32)).cuda())
+        torch.cuda.synchronize()
+        lam, v = lam.cpu().numpy().astype(np.float64), v.cpu().numpy().astype(np.float64)
+        ref = np.linalg.eigvalsh(a)
+        scale = max(np.abs(ref).max(), 1e-30)
+        assert np.all(np.diff(lam) >= 0)                                            # ascending
+        # fp32 cyclic Jacobi: ~6 sweeps x (n-1) steps of rotations, a few 1e-6 |A| of accumulated rounding
+        assert np.abs(lam - ref).max() <= 2e-5 * scale, (n, np.abs(lam - ref).max() / scale)
+        assert np.abs(v.T @ v - np.eye(n)).max() < 5e-5
+        assert np.abs(v @ np.diag(lam) @ v.T - a).max() <= 5e-5 * scale
