@@ -972,7 +972,7 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         int sms = sm_count();
         if (sms <= 0) sms = 148;
         const size_t q_tiles_in_flight = (size_t)sms * TC_BM * L.width * 2;
-        tp.split_major = (L.n_splits > 1 && q_tiles_in_flight > ((size_t)48 << 20)) ? 1 : 0;
+        tp.split_major = (L.n_splits > 1 && q_tiles_in_flight > ((size_t)48 << 20) && L.n_qblocks <= 65535) ? 1 : 0;   // grid.y limit
     }
     tp.window_begin = 0;
     tp.window_tiles = L.tiles_per_split;
