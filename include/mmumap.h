@@ -288,6 +288,25 @@ int mmu_infonce_bidir(const float *e0, const float *e1, int64_t num, int64_t anc
 int mmu_adam_step(float *p, float *g, float *m, float *v, int64_t n, double beta1, double beta2,
                   double eps, const uint32_t *state, int zero_grad, mmu_stream_t stream);
 
+/* ----------------------------------------------------------------------------------
+ * Multi-GPU optimiser step over NVLink peer memory (one process per GPU; the reference is single-process,
+ * this is the exchange SURVEY.md 8(e) derives for model.py:439-476 sharded by edges).
+ * The W ranks hold replicas of the flat parameter buffer and partial gradients in buffers that are mapped
+ * into every rank's address space (peer_*[w] = device pointer, valid on THIS rank, to rank w's buffer).
+ * mmu_adam_step_peer: rank r sums the r-th 1/W shard of all W gradient buffers in rank order, applies
+ *   mmu_adam_step's arithmetic to it and writes the new parameters into all W parameter replicas; m / v are
+ *   local, full-size (only the shard is touched).  It neither waits for peers nor clears gradients:
+ * mmu_peer_barrier: flag barrier between the W ranks in symmetric memory (peer_flags[w] -> 2 x MMU_PEER_MAX
+ *   uint32 of rank w, zero-initialised; slot 0 / 1; seq must increase by one per use of a slot).  Call it with
+ *   slot 0 after the gradient kernels and before mmu_adam_step_peer, with slot 1 after it; the local gradient
+ *   buffer may be cleared after the slot-1 barrier.  A peer that does not arrive within 20 s fails the launch.
+ * ---------------------------------------------------------------------------------- */
+#define MMU_PEER_MAX 16
+int mmu_peer_barrier(const uint64_t *peer_flags, int world, int rank, int slot, uint32_t seq, mmu_stream_t stream);
+int mmu_adam_step_peer(const uint64_t *peer_params, const uint64_t *peer_grads, float *m, float *v, int64_t n,
+                       int world, int rank, double beta1, double beta2, double eps, const uint32_t *state,
+                       mmu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,9 @@ def replay_infonce_draws(num: int):
     return perm.to(torch.int32), neg.to(torch.int32)
 
 
+_PEER_CACHE: dict = {}
+
+
 class LayoutOptimizer:
     def __init__(self, embeds, graphs, a: float, b: float, num_rep: int, lr: float, alpha: float,
                  batch_size: int, mode: str = "fit", refs=None, sample_stream: str | None = None,
@@ -131,6 +134,7 @@ class LayoutOptimizer:
         total = sum(sizes)
         self.flat = tuple(torch.zeros(max(total, 1), dtype=torch.float32, device=dev) for _ in range(4))   # p, g, m, v
         self.total = total
+        self.peer = self._peer_setup(total, dev)      # multi-GPU: parameters and gradients in NVLink peer memory
         self.mods, off = [], 0
         for i, (e, g) in enumerate(zip(embeds, graphs)):
             self.mods.append(_Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
@@ -153,6 +157,56 @@ class LayoutOptimizer:
         self.losses: list[float] = []
         self.done = 0                  # epochs completed (== the device-side epoch counter)
         self.edge_updates = 0          # host-stream mode counts them exactly; device mode reads kept_count
+
+    def _peer_setup(self, total: int, dev):
+        """Multi-GPU (NCCL backend, one node): put the replicated parameter buffer and this rank's partial
+        gradient buffer into symmetric memory that every rank maps, so that the epoch's exchange is one kernel
+        over peer pointers (mmu_adam_step_peer) instead of an NCCL all-reduce plus a replicated Adam step.
+        Returns None (-> NCCL path) for one rank, other backends, MMUMAP_PEER_ADAM=0, or when the symmetric
+        allocation is not available on this system."""
+        import torch.distributed as dist
+        w = D.world()
+        if (w == 1 or w > native.PEER_MAX or total == 0 or os.environ.get("MMUMAP_PEER_ADAM", "1") != "1"
+                or dist.get_backend() != "nccl"):
+            return None
+        import ctypes
+        pr = _PEER_CACHE.get("buf")
+        if pr is False:                                                # tried before, not available
+            return None
+        if pr is None or pr["cap"] < total:
+            # one symmetric allocation per process, reused by later optimisers (fit, then transform): the
+            # rendezvous exchanges memory handles through the store and is not free
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            sym = hdl = None
+            cap = -(-total // 65536) * 65536
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                n_flags = 2 * native.PEER_MAX                          # uint32 flags, kept in the tail of the buffer
+                sym = symm_mem.empty(2 * cap + n_flags, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+                sym.zero_()
+            except Exception as exc:                                   # noqa: BLE001 - any failure means "not available"
+                if D.rank() == 0:
+                    print(f"umap_b200: symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce",
+                          flush=True)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)                  # all ranks take the same path
+            if int(ok.item()) == 0:
+                _PEER_CACHE["buf"] = False
+                return None
+            torch.cuda.synchronize()
+            dist.barrier()                                             # every rank's flags are zero before the first use
+            bases = [int(b) for b in hdl.buffer_ptrs]
+            arr = ctypes.c_uint64 * w
+            pr = {"sym": sym, "hdl": hdl, "seq": 0, "cap": cap,
+                  "params": arr(*bases), "grads": arr(*[b + 4 * cap for b in bases]),
+                  "flags": arr(*[b + 8 * cap for b in bases])}
+            _PEER_CACHE["buf"] = pr
+        sym, cap = pr["sym"], pr["cap"]
+        # the previous user's last epoch ended with the slot-1 barrier: no peer still reads these buffers
+        sym[cap:cap + total].zero_()
+        self.flat = (sym[:total], sym[cap:cap + total], self.flat[2], self.flat[3])
+        return pr
 
     # ------------------------------------------------------------------ one epoch
     def _forces(self, mod: _Modality, kept_pos, kept_count, neg, batch_kept):
@@ -267,13 +321,26 @@ class LayoutOptimizer:
                     sid += 2
 
     def _adam_tail(self):
-        # multi-GPU: one all-reduce of the flat gradient buffer, then the identical Adam step everywhere
-        D.all_reduce_sum(self.flat[1])
-        check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
         p, g, m, v = self.flat
-        with profiler.stage("adam", level=2):
-            check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
-                                      stream()), "mmu_adam_step")
+        if self.peer is not None:
+            # multi-GPU over peer memory: [all gradients complete] -> reduce my shard + Adam + write all replicas
+            # -> [all parameters delivered] -> clear my gradient buffer
+            pr, w, r = self.peer, D.world(), D.rank()
+            pr["seq"] += 1
+            check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
+            with profiler.stage("adam", level=2):
+                check(lib().mmu_peer_barrier(pr["flags"], w, r, 0, pr["seq"], stream()), "mmu_peer_barrier")
+                check(lib().mmu_adam_step_peer(pr["params"], pr["grads"], ptr(m), ptr(v), self.total, w, r, BETA1, BETA2,
+                                               EPS, ptr(self.state), stream()), "mmu_adam_step_peer")
+                check(lib().mmu_peer_barrier(pr["flags"], w, r, 1, pr["seq"], stream()), "mmu_peer_barrier")
+                g.zero_()
+        else:
+            # (NCCL path) one all-reduce of the flat gradient buffer, then the identical Adam step everywhere
+            D.all_reduce_sum(g)
+            check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
+            with profiler.stage("adam", level=2):
+                check(lib().mmu_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), self.total, BETA1, BETA2, EPS, ptr(self.state), 1,
+                                          stream()), "mmu_adam_step")
         self.done += 1
         if self.loss is not None:
             D.all_reduce_sum(self.loss)
@@ -356,7 +423,7 @@ class LayoutOptimizer:
         small = sum(m.graph.nnz for m in self.mods) <= 1_000_000        # epochs of a few tens of microseconds
         use_graph = (self.sample_stream == "device" and self.loss is None and epochs > 2
                      and (mode == "1" or (mode == "auto" and small))
-                     and (D.world() == 1 or os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1"))
+                     and (D.world() == 1 or (self.peer is None and os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1")))
         if not use_graph:
             overlap = (self.sample_stream == "device" and not self.use_records and self.mode in ("fit", "transform")
                        and epochs > 1 and os.environ.get("MMUMAP_OVERLAP_SAMPLE", "1") == "1")

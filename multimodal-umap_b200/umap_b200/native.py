@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libmmumap_b200.so")
 MAX_K = 64
 KNN_TC_MAX_K = 32
 OPT_STATE_WORDS = 8
+PEER_MAX = 16
 SIGMA_BISECT = 0
 SIGMA_NEWTON = 1
 
@@ -49,6 +50,9 @@ _SIGNATURES = {
     "mmu_spmm_csr_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float, c_void_p,
                                    c_float, c_void_p, c_void_p]),
     "mmu_eigh_small": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "mmu_adam_step_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, c_double,
+                                   c_double, c_void_p, c_void_p]),
     "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
     "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
     "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,

@@ -43,6 +43,16 @@ def run(sharded):
         opt = LayoutOptimizer([y0, y1], [sym, sym2], 1.577, 0.8951, 8, 0.01, 1.0, 256, mode="fit", sample_stream="device", seed=3)
         out = opt.run(5)
         kept = opt.kept_last_epoch()
+        if sharded:
+            # the replicas must be bit-identical on every rank (peer path: each parameter is computed once and
+            # copied; NCCL path: the same all-reduced gradient everywhere)
+            flat = torch.cat([o.reshape(-1) for o in out]).view(torch.int32)
+            ref = flat.clone()
+            dist.broadcast(ref, src=0)
+            same = bool(torch.equal(flat, ref))
+            print(f"[rank {rank}] exchange = {'peer memory (mmu_adam_step_peer)' if opt.peer is not None else 'NCCL all-reduce'}; "
+                  f"replica identical to rank 0 = {same}", flush=True)
+            assert same
     finally:
         if not sharded:
             D.world, D.rank = saved
