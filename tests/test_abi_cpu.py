@@ -117,3 +117,22 @@ def test_ab_coefficients_match_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "ab.npz"))
     m = model.UMAPMixture(k_neighbors=15, out_dim=2, min_dist=0.1, num_encoders=1)
     assert abs(m.a - float(g["a"])) < 2e-4 and abs(m.b - float(g["b"])) < 2e-4
+
+
+def test_peer_entry_points_validate_arguments():
+    """mmu_peer_barrier / mmu_adam_step_peer (include/mmumap.h: multi-GPU optimiser step over peer memory)
+    reject bad geometry before any launch."""
+    from umap_b200 import native
+    lib = native.lib()
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.addressof(buf)
+    ptrs = (ctypes.c_uint64 * 2)(p & ~15, (p & ~15) + 64)
+    assert lib.mmu_peer_barrier(ptrs, 2, 2, 0, 1, None) == 1 and b"world/rank" in lib.mmu_last_error()
+    assert lib.mmu_peer_barrier(ptrs, 2, 0, 2, 1, None) == 1 and b"slot" in lib.mmu_last_error()
+    assert lib.mmu_peer_barrier(ptrs, native.PEER_MAX + 1, 0, 0, 1, None) == 1
+    bad = (ctypes.c_uint64 * 2)(p & ~15, 0)
+    assert lib.mmu_peer_barrier(bad, 2, 0, 0, 1, None) == 1 and b"peer pointer" in lib.mmu_last_error()
+    assert lib.mmu_adam_step_peer(ptrs, ptrs, p & ~15, p & ~15, 6, 2, 0, 0.9, 0.999, 1e-8, p, None) == 1
+    assert b"multiple of 4" in lib.mmu_last_error()
+    assert lib.mmu_eigh_small(None, 4, None, None, None) == 1
+    assert lib.mmu_eigh_small(p, 65, p, p, None) == 1 and b"n=65" in lib.mmu_last_error()
