@@ -92,7 +92,12 @@ int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_
  * fallback_rows with min_splits = 8 and precision = 1 before resorting to the exhaustive kernel).
  * precision 0: fp16 operands (error bound ~2^-9 |x||y| on a score).  precision 1: error-compensated
  * split operands hi + lo (three times the MMA work, error bound ~2^-20 |x||y|) for data whose
- * neighbour gaps are small against |x||y| (low dimension, norms large against local distances). */
+ * neighbour gaps are small against |x||y| (low dimension, norms large against local distances).
+ * Kernel form (chosen by the call, same results): rows of padded width >= 512 run as CTA pairs
+ * (tcgen05.mma.cta_group::2, M = 256: two query blocks share each database tile, each SM stages half
+ * of it), and a database that does not fit in L2 is then walked in ~48 MB windows, one launch per
+ * window, the per-row candidate lists carried between launches in the workspace; shorter rows use
+ * one CTA per query block (cta_group::1, M = 128). */
 #define MMU_KNN_TC_MAX_K 32
 size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits,
                                   int precision);
