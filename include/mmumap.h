@@ -50,6 +50,19 @@ uint64_t mmu_launch_count(void);
 void mmu_launch_count_add(uint64_t n);
 /* Device properties the host uses to size persistent grids. Synchronous. */
 int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+/* A/B switches of the kernels (measurement and tests only; results never depend on them).  They are read from
+ * the environment ONCE when the library is loaded and can be changed afterwards with mmu_set_option:
+ *   "force_staged"  (env MMUMAP_FORCE_RUNS,     default 1)  0 = plain loop force kernel instead of the staged run form
+ *   "knn_cta_pairs" (env MMUMAP_KNN_CTA_PAIRS,  default 1)  0 = one CTA per query block instead of cta_group::2 pairs
+ *   "knn_window_mb" (env MMUMAP_KNN_WINDOW_MB,  default -1) -1 = automatic, 0 = one launch, >0 = database window size
+ *   "sgd_window_mb" (env MMUMAP_SGD_WINDOW_MB,  default -1) host hint for mmu_edge_forces' window_rows (-1 = automatic)
+ *   "knn_fold_norms" (env MMUMAP_KNN_FOLD_NORMS, default 1) 0 = add |Y|^2 in the epilogue instead of inside the contraction
+ * Unknown names return MMU_ERR_ARG. */
+int mmu_set_option(const char *name, int64_t value);
+int mmu_get_option(const char *name, int64_t *value);
+/* Name of the kernel variant the given launch site chose last ("knn_candidates", "edge_forces", "epoch_tail",
+ * "block_ops", ...; "" if it has not launched): bench.py reports what actually ran instead of a constant. */
+const char *mmu_last_kernel(const char *site);
 
 /* ------------------------------------------------------------------------------------
  * K1/K2/K3  exact kNN graph            ref: model.py:81-195 (candidate search + per-row
@@ -179,30 +192,35 @@ int mmu_opt_state_init(uint32_t *state, mmu_stream_t stream);
  * bc2_sqrt = sqrt(1-beta2^step) in double precision. */
 int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, double beta2, mmu_stream_t stream);
 
-/* K7a (device sample stream): Bernoulli(w) keep per edge (ref: model.py:432) with a
- * counter-based Philox4x32-10 stream keyed by (seed, state->epoch, edge position).  Writes the
- * kept edge positions (any order) to kept_pos, their number to *kept_count and the number
- * kept in each row-batch (ref: model.py:423-424, batch = row / batch_size) to batch_kept.
- * kept_count and batch_kept are zeroed by this call. */
-int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
-                    uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
-                    int32_t *batch_kept, mmu_stream_t stream);
-
-/* The same for the edges [edge_lo, edge_hi) of the COO only (edge-sharded multi-GPU optimisation):
- * kept_pos holds GLOBAL edge positions and the random stream is keyed on global positions, so the
- * union over shards equals what mmu_edge_sample draws on one GPU. */
-int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
-                          int batch_size, int n_batches, uint64_t seed, const uint32_t *state,
-                          int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept,
+/* Kept-edge list of one epoch: `kept_rec` holds one 16-byte record {edge position, row, col, row-batch} per kept
+ * edge (4 x int32, 16-byte aligned), `kept_hdr` (4 x int32 on the device) is its header: [0] number of kept
+ * edges (written by the sampler / mmu_edge_records), [1] capacity of kept_rec in records (written by the HOST once,
+ * before the first call), [2] overflow flag (set when an epoch kept more edges than the capacity: the surplus is
+ * dropped and the host must treat the run as failed), [3] reserved.
+ *
+ * K7a (device sample stream): Bernoulli(w) keep per edge (ref: model.py:432) with a counter-based Philox4x32-10
+ * stream keyed by (seed, state->epoch, edge position), for the edges [edge_lo, edge_hi) of the COO (the whole graph,
+ * or one rank's shard of an edge-sharded multi-GPU optimisation: positions are GLOBAL and the random stream is keyed
+ * on them, so the union over shards equals what one GPU draws).  Writes the records of the kept edges (row sorted
+ * inside every 1024-edge chunk, chunks in any order) and the number kept in each row-batch (ref: model.py:423-424,
+ * batch = row / batch_size) to batch_kept.  kept_hdr[0] and batch_kept are zeroed by the call. */
+int mmu_edge_sample_range(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                          int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
+                          const uint32_t *state, int32_t *kept_rec, int32_t *kept_hdr, int32_t *batch_kept,
                           mmu_stream_t stream);
 
 /* The same with the epoch number given by the host (epoch >= 0) instead of read from `state`:
  * lets the sampling of epoch e+1 run on a second stream while the forces of epoch e execute (it
  * does not depend on the embeddings).  epoch = -1 reads state->epoch. */
-int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
-                       int batch_size, int n_batches, uint64_t seed, int64_t epoch,
-                       const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
-                       int32_t *batch_kept, mmu_stream_t stream);
+int mmu_edge_sample_at(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                       int64_t edge_hi, int batch_size, int n_batches, uint64_t seed, int64_t epoch,
+                       const uint32_t *state, int32_t *kept_rec, int32_t *kept_hdr, int32_t *batch_kept,
+                       mmu_stream_t stream);
+
+/* Host sample stream: kept_pos [n_kept] are the edge positions the replayed CPU draws kept (ref: model.py:432,
+ * in the reference's order); builds their records and sets kept_hdr[0] = n_kept. */
+int mmu_edge_records(const int32_t *row, const int32_t *col, const int32_t *kept_pos, int64_t n_kept,
+                     int batch_size, int32_t *kept_rec, int32_t *kept_hdr, mmu_stream_t stream);
 
 /* K7b: forces of every kept edge and its num_rep negatives, accumulated with red.global.add
  * into the gradient table(s).  Gradient of
@@ -211,37 +229,25 @@ int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int6
  * head/grad_head: the table being optimised [n_head x dim]; tail: table the column indices
  * and negatives address (same pointer as head in fit mode, the frozen fitted table in
  * transform mode); grad_tail: NULL in transform mode (ref: model.py:399-401,416).
- * neg: [n_kept x num_rep] host-generated negative ids (ref: model.py:444) or NULL to draw
- * them on the device (Philox, uniform in [0, rep_count)).
- * kept_count: device scalar (number of valid entries of kept_pos).
+ * neg: [n_kept x num_rep] host-generated negative ids (ref: model.py:444) in kept-list order, or NULL to
+ * draw them on the device (Philox keyed on the edge position, uniform in [0, rep_count)).
  * loss (nullable): device float accumulating the modality's loss.
  * fast_math != 0: s^b through ex2/lg2 and an approximate reciprocal (relative error of a force
  * coefficient <= ~1e-5; meant for the device sample stream); 0 = powf and IEEE division, the
- * arithmetic the parity tests pin to the reference. */
-int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
-                    const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
-                    int n_batches, int batch_size, int num_rep, int64_t rep_count,
-                    const float *head, const float *tail, float *grad_head, float *grad_tail,
-                    int dim, float a, float b, uint64_t seed, const uint32_t *state, float *loss,
-                    int fast_math, mmu_stream_t stream);
-
-/* Record form of K7a/K7b (device sample stream): the sampler writes one 16-byte record
- * {edge position, row, col, row-batch} per kept edge (kept_rec: 4 x int32 per edge, 16-byte
- * aligned, capacity edge_hi - edge_lo) and the force kernel starts each edge from that single
- * sequential load (prefetched one iteration ahead) instead of the kept_pos -> row/col pointer
- * chase.  Same sampling stream and arithmetic as mmu_edge_sample_range / mmu_edge_forces with
- * neg = NULL.  Supported for dim in {2,4,8,16,32,64,128} and num_rep in {4,8}
- * (mmu_edge_forces_records_supported). */
-int mmu_edge_sample_records(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
-                            int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
-                            const uint32_t *state, int32_t *kept_rec, int32_t *kept_count,
-                            int32_t *batch_kept, mmu_stream_t stream);
-int mmu_edge_forces_records_supported(int dim, int num_rep);
-int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *kept_count, const int32_t *batch_kept,
-                            int n_batches, int num_rep, int64_t rep_count, const float *head,
-                            const float *tail, float *grad_head, float *grad_tail, int dim, float a,
-                            float b, uint64_t seed, const uint32_t *state, float *loss, int fast_math,
-                            mmu_stream_t stream);
+ * arithmetic the parity tests pin to the reference.
+ * window_rows > 0 (and < rep_count): the tail table is processed in windows of that many rows, one launch per
+ * window over the whole kept list, each launch handling only the (edge, tail) pairs whose tail row lies in its
+ * window -- for tables that do not fit the L2 (10M x 2-D: every random 8-byte gather / red would otherwise move
+ * a 32-byte DRAM sector), so that the random traffic of a pass stays inside an L2-resident slice.  Same pairs,
+ * same arithmetic; only the order of the atomics differs.  0 = one pass.
+ * Kernel form: dim in {2,4,8,16,32,64,128} with num_rep in {4,8} runs the staged run-form kernel (records
+ * staged through shared memory with cp.async, head gradient accumulated per run of equal rows); other
+ * (dim, num_rep), or option force_staged = 0, the plain loop kernels.  mmu_last_kernel("edge_forces") names it. */
+int mmu_edge_forces(const int32_t *kept_rec, const int32_t *kept_hdr, const int32_t *neg,
+                    const int32_t *batch_kept, int n_batches, int num_rep, int64_t rep_count,
+                    const float *head, const float *tail, float *grad_head, float *grad_tail, int dim,
+                    float a, float b, uint64_t seed, const uint32_t *state, float *loss, int fast_math,
+                    int64_t window_rows, mmu_stream_t stream);
 
 /* K7c: invert-mode forces (inverse_transform).            ref: model.py:336-362, :437, :447
  * head / grad_head: the Q x dim table being reconstructed in DATA space; data [n x dim]: the
@@ -249,12 +255,11 @@ int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *kept_count, 
  * Gradient of mean_batches[ mean_kept dist/(w sigma_j + 1e-6)
  *                          + mean_{kept*R} -log(1 - exp(-max(dist - rho_l, 1e-6)/(sigma_l+1e-6)) + 1e-6) ],
  * dist = sqrt(max(|x_i - y|^2, 1e-6)), w = 1/(1 + a dist^(2b)).  Other arguments as mmu_edge_forces. */
-int mmu_invert_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
-                      const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
-                      int n_batches, int batch_size, int num_rep, int64_t rep_count, const float *head,
-                      const float *data, const float *sigma, const float *rho, float *grad_head, int dim,
-                      float a, float b, uint64_t seed, const uint32_t *state, float *loss,
-                      mmu_stream_t stream);
+int mmu_invert_forces(const int32_t *kept_rec, const int32_t *kept_hdr, const int32_t *neg,
+                      const int32_t *batch_kept, int n_batches, int num_rep, int64_t rep_count,
+                      const float *head, const float *data, const float *sigma, const float *rho,
+                      float *grad_head, int dim, float a, float b, uint64_t seed, const uint32_t *state,
+                      float *loss, mmu_stream_t stream);
 
 /* K8: InfoNCE gradient for one direction (anchors e0 -> positives/negatives e1).
  * ref: model.py:364-394.  perm [num] (nullable = identity) and neg [num x n_neg] (nullable =
@@ -311,6 +316,16 @@ int mmu_peer_barrier(const uint64_t *peer_flags, int world, int rank, int slot, 
 int mmu_adam_step_peer(const uint64_t *peer_params, const uint64_t *peer_grads, float *m, float *v, int64_t n,
                        int world, int rank, double beta1, double beta2, double eps, const uint32_t *state,
                        mmu_stream_t stream);
+
+/* ----------------------------------------------------------------------------------
+ * Measured roof of the random-access kernels (reported by bench.py beside the HBM copy peak; not on the fit path).
+ * Touches n_rows_touched uniformly random rows of a [n_rows x row_floats] table the way mmu_edge_forces does: one
+ * 16-byte vector load per lane and row from `table` (do_gather) and/or one 16-byte vector red per lane and row into
+ * `accum` (do_red), 8 rows in flight per group of row_floats/4 lanes, no arithmetic.  row_floats in {2,4,16,64}.
+ * Bytes moved = n_rows_touched * row_floats * 4 * (do_gather + do_red).  ref: the gathers / index_put_ of
+ * model.py:316-321,328-333 and their backward. */
+int mmu_roof_random_rows(const float *table, float *accum, int64_t n_rows, int row_floats, int64_t n_rows_touched,
+                         uint64_t seed, int do_gather, int do_red, float *sink, mmu_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,16 @@ void count_launch(int n);   // n of OUR kernels were launched (mmu_launch_count)
 
 int sm_count();   // cached; 0 when no device
 
+// launch sites with per-device one-time setup and/or a reported kernel variant (mmu_last_kernel)
+enum : int { SITE_KNN_CANDIDATES = 0, SITE_KNN_EXACT, SITE_EIGH_SMALL, SITE_EDGE_FORCES, SITE_EPOCH_TAIL, SITE_BLOCK_OPS,
+             MMU_SITE_COUNT };
+bool first_use_on_device(int site);                  // true exactly once per (site, current device)
+void note_kernel(int site, const char *fmt, ...);    // name of the kernel variant the site launched last
+
+// A/B switches: read from the environment once at load, changed with mmu_set_option (never getenv per launch)
+enum : int { OPT_FORCE_STAGED = 0, OPT_KNN_CTA_PAIRS, OPT_KNN_WINDOW_MB, OPT_SGD_WINDOW_MB, OPT_KNN_FOLD_NORMS, OPT_COUNT };
+long long option(int id);
+
 static inline cudaStream_t as_stream(mmu_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------- optimiser state words

@@ -136,12 +136,9 @@ extern "C" int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_s
     MMU_CHECK_ARG(n >= 1 && n <= EIGH_MAX_N, "mmu_eigh_small: n=%d outside [1,%d]", n, EIGH_MAX_N);
     const int ne = (n + 1) & ~1;
     const size_t smem = sizeof(float) * ((size_t)4 * n * n + 2 * ne + n);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(SITE_EIGH_SMALL))     // the attribute is per device
         MMU_CUDA(cudaFuncSetAttribute(eigh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(float) * (4 * EIGH_MAX_N * EIGH_MAX_N + 4 * EIGH_MAX_N))));
-        attr_set = true;
-    }
     eigh_small_kernel<<<1, EIGH_THREADS, smem, as_stream(stream)>>>(a, n, lam, v);
     MMU_LAUNCH_CHECK();
     return MMU_OK;

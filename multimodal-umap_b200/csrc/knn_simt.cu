@@ -191,11 +191,8 @@ extern "C" int mmu_knn_exact_f32(const float *query, int64_t n_query, const int3
     MMU_CHECK_ARG(n_db + db_index_base < (int64_t)2147483647, "mmu_knn_exact_f32: db index exceeds int32");
     if (n_query == 0) return MMU_OK;
     size_t smem = sizeof(float) * REGION_A_FLOATS + sizeof(uint64_t) * (size_t)BQ * k;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(SITE_KNN_EXACT))      // the attribute is per device
         MMU_CUDA(cudaFuncSetAttribute(knn_exact_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = true;
-    }
     int64_t grid = (n_query + BQ - 1) / BQ;
     knn_exact_f32_kernel<<<(unsigned)grid, KNN_THREADS, smem, as_stream(stream)>>>(
         query, n_query, query_ids, db, n_db, dim, k, exclude_self, query_index_base, db_index_base,

@@ -939,9 +939,8 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     MMU_LAUNCH_CHECK_N(launches);
 
     // ---- candidates
-    // CTA pairs (cta_group::2) for long rows; MMUMAP_KNN_CTA_PAIRS=0 keeps one CTA per query block (A/B measurements)
-    const char *pe = getenv("MMUMAP_KNN_CTA_PAIRS");
-    const int pairs_allowed = (pe && pe[0] == '0') ? 0 : 1;
+    // CTA pairs (cta_group::2) for long rows; option knn_cta_pairs = 0 keeps one CTA per query block (A/B measurements)
+    const int pairs_allowed = option(OPT_KNN_CTA_PAIRS) != 0;
     // Short rows (width < 512: at most 7 k-blocks per tile) are bound by the per-tile epilogue, not by operand
     // traffic; there a pair only couples the two epilogues (1M x 128, k = 30: 795 ms paired, 695 ms unpaired).
     const int ncta = (pairs_allowed && L.n_qblocks >= 2 && L.width >= 512) ? 2 : 1;
@@ -950,13 +949,11 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     if (rc) return rc;
     rc = make_map(&tm_db, db16, L.n_pad, L.width, TC_BN / ncta);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(SITE_KNN_CANDIDATES)) {     // the attribute is per device
         MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<1>::SMEM_BYTES));
         MMU_CUDA(cudaFuncSetAttribute(knn_tc_candidates_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<2>::SMEM_BYTES));
-        attr_set = true;
     }
     TcParams tp;
     tp.ynorm = ynorm;
@@ -984,11 +981,12 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         // one launch per window over ALL query blocks; the lists carry over through cand_idx / cand_score.
         const size_t tile_bytes = (size_t)TC_BN * L.width * 2;
         const size_t region = (size_t)L.n_splits * L.tiles_per_split * tile_bytes;
-        // MMUMAP_KNN_WINDOW_MB: window size; set explicitly it applies to every pair launch (tests), 0 = one launch
-        const char *e = getenv("MMUMAP_KNN_WINDOW_MB");
-        const long window_mb = e ? atol(e) : 48;
+        // option knn_window_mb: window size; set explicitly (>= 0) it applies to every pair launch (tests), 0 = one launch
+        const long long wopt = option(OPT_KNN_WINDOW_MB);
+        const bool forced = wopt >= 0;
+        const long long window_mb = forced ? wopt : 48;
         // (split-major launches keep few query blocks and every split in flight; measured fine as one launch)
-        if (window_mb > 0 && (e || (region > ((size_t)160 << 20) && !tp.split_major))) {
+        if (window_mb > 0 && (forced || (region > ((size_t)160 << 20) && !tp.split_major))) {
             size_t w = ((size_t)window_mb << 20) / ((size_t)L.n_splits * tile_bytes);
             tp.window_tiles = (int)(w < 8 ? 8 : w);
             if (tp.window_tiles > L.tiles_per_split) tp.window_tiles = L.tiles_per_split;

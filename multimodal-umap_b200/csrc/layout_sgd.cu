@@ -29,14 +29,19 @@ __global__ void opt_state_advance_kernel(OptState *s, double lr, double beta1, d
     s->bc2_sqrt = (float)sqrt(bc2);
 }
 
+
 // ------------------------------------------------------------------ K7a: edge sampling
+// Kept-edge list header (device, 4 x int32): [0] number of kept edges, [1] capacity of the record array (written
+// by the host once), [2] overflow flag (set when an epoch kept more than the capacity; the host checks it).
+// One 16-byte record per kept edge: {edge position, row, col, row-batch}.  The force kernels start every edge
+// from this single sequential load (staged through shared memory) instead of a kept_pos -> row/col chase.
+//
 // thread handles 4 consecutive edges (one Philox call -> 4 uniforms)
-template <bool REC>
 __global__ void __launch_bounds__(256)
 edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, const float *__restrict__ w,
                    int64_t edge_lo, int64_t nnz, int batch_size, uint64_t seed, const OptState *__restrict__ st,
-                   int32_t *__restrict__ kept_pos, int4 *__restrict__ kept_rec, int32_t *__restrict__ kept_count,
-                   int32_t *__restrict__ batch_kept, int64_t epoch_override) {
+                   int4 *__restrict__ kept_rec, int32_t *__restrict__ kept_hdr, int32_t *__restrict__ batch_kept,
+                   int64_t epoch_override) {
     // edges [edge_lo, nnz) of the global COO; the Philox counter is the GLOBAL quad index, so a
     // shard draws exactly what the single-GPU run draws for the same edges
     const uint32_t epoch = epoch_override >= 0 ? (uint32_t)epoch_override : st->epoch;
@@ -44,6 +49,7 @@ edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n4 = (nnz + 3) >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int cap = kept_hdr[1];
     __shared__ int s_wtot[8];
     __shared__ int s_base;
     // every thread of a block iterates the same number of times (block-level compaction below)
@@ -87,16 +93,13 @@ edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
             int tot = 0;
 #pragma unroll
             for (int u = 0; u < 8; ++u) { int t = s_wtot[u]; s_wtot[u] = tot; tot += t; }
-            s_base = tot ? atomicAdd(kept_count, tot) : 0;
+            s_base = tot ? atomicAdd(&kept_hdr[0], tot) : 0;
+            if (tot && s_base + tot > cap) kept_hdr[2] = 1;                       // more kept edges than the list holds
         }
         __syncthreads();
         const int off = s_base + s_wtot[warp] + incl - cnt;
-        for (int i = 0; i < cnt; ++i) {
-            // REC: one 16-byte record {edge position, row, col, row-batch} per kept edge, so that the force
-            // kernel starts from a single sequential load instead of a kept_pos -> row/col pointer chase
-            if (REC) kept_rec[off + i] = make_int4(pos[i], erow[i], col[pos[i]], brow[i]);
-            else kept_pos[off + i] = pos[i];
-        }
+        for (int i = 0; i < cnt; ++i)
+            if (off + i < cap) kept_rec[off + i] = make_int4(pos[i], erow[i], col[pos[i]], brow[i]);
         // per-batch counts, aggregated on the warp's most common batch (edges are row sorted)
         unsigned has = __ballot_sync(0xffffffffu, cnt > 0);
         int src_lane = has ? __ffs(has) - 1 : 0;
@@ -111,6 +114,19 @@ edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
         if (lane == 0 && same) atomicAdd(&batch_kept[b_ref], same);
         __syncthreads();                                                          // s_wtot / s_base reused next iteration
     }
+}
+
+// host sample stream: the kept positions come from the replayed CPU draws; build their records
+__global__ void __launch_bounds__(256)
+edge_records_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                    const int32_t *__restrict__ kept_pos, int64_t n_kept, int batch_size, int4 *__restrict__ kept_rec,
+                    int32_t *__restrict__ kept_hdr) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) { kept_hdr[0] = (int32_t)n_kept; kept_hdr[2] = n_kept > kept_hdr[1] ? 1 : 0; }
+    if (e >= n_kept || e >= kept_hdr[1]) return;
+    const int32_t p = kept_pos[e];
+    const int32_t r = row[p];
+    kept_rec[e] = make_int4(p, r, col[p], r / batch_size);
 }
 
 // ------------------------------------------------------------------ K7b: forces
@@ -131,6 +147,15 @@ __device__ __forceinline__ Vec<VEC> load_vec(const float *p) {
     if (VEC == 4) { float4 t = *reinterpret_cast<const float4 *>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
     else if (VEC == 2) { float2 t = *reinterpret_cast<const float2 *>(p); r.v[0] = t.x; r.v[1] = t.y; }
     else { r.v[0] = *p; }
+    return r;
+}
+// L2-only load (ld.global.cg): random tail rows of a table larger than L1 only pollute it
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> load_vec_cg(const float *p) {
+    Vec<VEC> r;
+    if (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4 *>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; }
+    else if (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2 *>(p)); r.v[0] = t.x; r.v[1] = t.y; }
+    else { r.v[0] = __ldcg(p); }
     return r;
 }
 template <int VEC>
@@ -156,18 +181,20 @@ __device__ __forceinline__ void rep_terms(float s_raw, float a, float b, float &
     coef = (s_raw >= 1e-6f) ? -(2.0f * a * b * sb / s) / (f * (1.0f + q) * (1.0f + q)) : 0.0f;
 }
 
-// One group of LANES threads per kept edge; each thread owns VEC consecutive components
-// (dim == LANES*VEC), or, in the generic kernel (VEC==0), a warp per edge with strided components.
+__device__ __forceinline__ int kept_total(const int32_t *__restrict__ hdr) { return min(hdr[0], hdr[1]); }
+
+// Plain loop form: one group of LANES threads per kept edge (grid-stride), each thread owns VEC consecutive
+// components (dim == LANES*VEC), any num_rep.  The A/B partner of the staged kernel below (option force_staged = 0)
+// and the path of num_rep values it has no instantiation for.
 template <int VEC, int LANES>
 __global__ void __launch_bounds__(256)
-edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                   const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+edge_forces_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict__ kept_hdr,
                    const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
-                   int batch_size, int num_rep, uint32_t rep_count, const float *__restrict__ head,
+                   int num_rep, uint32_t rep_count, const float *__restrict__ head,
                    const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
                    int dim, float a, float b, uint64_t seed, const OptState *__restrict__ st,
                    float *__restrict__ loss_out) {
-    const int n_kept = *kept_count;
+    const int n_kept = kept_total(kept_hdr);
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int gl = threadIdx.x % LANES;
@@ -181,13 +208,12 @@ edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
     for (int64_t e0 = wfirst; e0 < n_kept; e0 += n_groups) {
         const int64_t e = e0 + (gid - wfirst);
         const bool active = e < n_kept;
-        int32_t i = 0, j = 0;
+        int32_t p = 0, i = 0, j = 0;
         float sc_a = 0.f, sc_r = 0.f;
         if (active) {
-            int32_t p = kept_pos[e];
-            i = row[p];
-            j = col[p];
-            float kb = (float)batch_kept[i / batch_size];
+            const int4 rec = kept_rec[e];
+            p = rec.x; i = rec.y; j = rec.z;
+            float kb = (float)batch_kept[rec.w];
             sc_a = inv_nb / kb;                                      // mean over kept, mean over batches
             sc_r = inv_nb / (kb * (float)num_rep);
         }
@@ -219,10 +245,7 @@ edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
             if (neg) {
                 l_idx = active ? (uint32_t)neg[e * num_rep + r] : 0u;
             } else {
-                if ((r & 3) == 0) {
-                    uint32_t p = active ? (uint32_t)kept_pos[e] : 0u;
-                    rnd = philox4x32_10(p, (uint32_t)(r >> 2), epoch, STREAM_NEG, k0, k1);
-                }
+                if ((r & 3) == 0) rnd = philox4x32_10((uint32_t)p, (uint32_t)(r >> 2), epoch, STREAM_NEG, k0, k1);
                 uint32_t x = (r & 3) == 0 ? rnd.x : (r & 3) == 1 ? rnd.y : (r & 3) == 2 ? rnd.z : rnd.w;
                 l_idx = urange(x, rep_count);
             }
@@ -249,14 +272,9 @@ edge_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
     }
 }
 
-// ------------------------------------------------------------------ K7b, register-blocked variant
-// Same arithmetic as edge_forces_kernel, reorganised for instruction throughput (ncu: the loop
-// version is XU/issue bound, not memory bound): all R+1 tail rows of an edge are gathered first
-// (R+1 independent 16-byte loads in flight per lane), the R+1 scalar force coefficients are split
-// over the LANES lanes of the group instead of being recomputed by each of them, and the
-// negatives' Philox call is split the same way.  FAST selects s^b = ex2(b*lg2(s)) and an
-// approximate reciprocal (device sample stream); !FAST keeps powf/div exactly as the loop version
-// (host-replayed stream, parity tests).
+// ------------------------------------------------------------------ K7b, staged run form (default)
+// FAST selects s^b = ex2(b*lg2(s)) and an approximate reciprocal (device sample stream); !FAST keeps
+// powf/div exactly as the loop version (host-replayed stream, parity tests).
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -283,112 +301,179 @@ __device__ __forceinline__ float pair_coef(float s_raw, bool attractive, float a
     }
 }
 
-// Run form of the kernel below: a group walks a CONTIGUOUS run of kept edges instead of a grid-stride set.  The
-// kept list is row sorted inside every sampler block's chunk, so consecutive edges mostly share their head row:
-// its gradient is accumulated in registers and leaves with ONE vector red per (run, row) instead of one per
-// edge, and the head row itself stays an L1 hit.  The kernel is bound by the L1->crossbar request port
-// (ncu: l1tex__m_l1tex2xbar_req_cycles_active 78-88 %), where every 64-byte red costs its payload cycles.
-template <int VEC, int LANES, int R, bool FAST>
+__device__ __forceinline__ void cp_async16_cg(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// records one group handles per round (runs of equal head rows are amortised over them) and the threads' share of
+// the shared-memory staging buffers: 2 x GROUPS x (T+1) records of 16 bytes, at most 40 KB per block
+template <int LANES>
+struct StageCfg {
+    static constexpr int T = LANES == 1 ? 4 : LANES == 2 ? 8 : 16;
+    static constexpr int GROUPS = 256 / LANES;
+    static constexpr int STRIDE = T + 1;           // one pad record per group: the groups' 16-byte reads hit distinct banks
+};
+
+// A block owns a contiguous, equal share of the kept list (row sorted inside every sampler block's chunk, so
+// consecutive records mostly share their head row) and walks it in rounds: all 256 threads copy the round's records
+// global -> shared with coalesced 16-byte cp.async (double buffered: round r+1 is in flight while round r is
+// processed), then every group of LANES lanes takes a contiguous run of `tr` <= T records out of shared memory.  The
+// head gradient of a run is accumulated in registers and leaves with ONE vector red per (run, row); the R+1 tail rows
+// of an edge are gathered first (R+1 independent 16-byte loads in flight per lane), the R+1 force coefficients are
+// evaluated by different lanes of the group and exchanged by shuffle, the negatives' Philox call is split the same way.
+//
+// WIN (tables larger than the L2: C4's 10M x 2-D p and g are 80 MB each, and a random 8-byte access moves a 32-byte
+// DRAM sector): the launch handles only the (edge, tail) pairs whose TAIL row lies in [win_lo, win_hi); the host
+// launches once per window, so that every random gather / red of a pass hits a slice of p and g that stays L2
+// resident, DRAM sees each table once per pass, and the kept records stream through.  The negatives are counter
+// based (Philox keyed on the edge position), so every pass regenerates the same draws: the same pairs, the same
+// arithmetic as the single pass -- only the order of the atomics changes.
+template <int VEC, int LANES, int R, bool FAST, bool WIN>
 __global__ void __launch_bounds__(256, 3)
-edge_forces_runs_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                        const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
-                        const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
-                        int batch_size, uint32_t rep_count, const float *__restrict__ head,
-                        const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
-                        float a, float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
+edge_forces_staged_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict__ kept_hdr,
+                          const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
+                          uint32_t rep_count, const float *__restrict__ head, const float *__restrict__ tail,
+                          float *__restrict__ grad_head, float *__restrict__ grad_tail, float a, float b, uint64_t seed,
+                          const OptState *__restrict__ st, float *__restrict__ loss_out, uint32_t win_lo, uint32_t win_len) {
+    using SC = StageCfg<LANES>;
     constexpr int DIM = VEC * LANES;
-    constexpr int NP = R + 1;
-    constexpr int NCALL = (R + 3) / 4;
+    constexpr int NP = R + 1;                                 // pairs per kept edge: 1 attractive + R repulsive
+    constexpr int NCALL = (R + 3) / 4;                        // Philox calls per edge
     constexpr int ROUNDS = (NP + LANES - 1) / LANES;
-    const int n_kept = *kept_count;
+    constexpr int T = SC::T, GROUPS = SC::GROUPS, STRIDE = SC::STRIDE;
+    __shared__ int4 s_rec[2][GROUPS * STRIDE];
+    const int n_kept = kept_total(kept_hdr);
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int gl = threadIdx.x % LANES;
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+    const int grp = threadIdx.x / LANES;
     const float inv_nb = 1.0f / (float)n_batches;
     const bool want_loss = loss_out != nullptr;
     float loss_acc = 0.f;
-    const int per = (int)((n_kept + n_groups - 1) / n_groups);      // run length: the same for every group
-    const int64_t e_begin = gid * per;
+    // this block's share, split into rounds of GROUPS x tr records with tr <= T as equal as possible
+    const int per_block = (int)(((int64_t)n_kept + gridDim.x - 1) / gridDim.x);
+    const int64_t blk_lo = (int64_t)blockIdx.x * per_block;
+    const int64_t blk_hi = min((int64_t)n_kept, blk_lo + per_block);
+    const int mine = blk_hi > blk_lo ? (int)(blk_hi - blk_lo) : 0;
+    const int n_rounds = (mine + GROUPS * T - 1) / (GROUPS * T);
+    const int tr = n_rounds ? (mine + n_rounds * GROUPS - 1) / (n_rounds * GROUPS) : 0;
+    const int per_round = tr * GROUPS;
+
+    auto issue = [&](int buf, int round) {
+        const int64_t base = blk_lo + (int64_t)round * per_round;
+        for (int r = threadIdx.x; r < per_round; r += 256) {
+            if (base + r < blk_hi) cp_async16_cg(&s_rec[buf][(r / tr) * STRIDE + (r % tr)], kept_rec + base + r);
+        }
+        cp_async_commit_group();
+    };
+    if (n_rounds) issue(0, 0);
     int32_t cur_i = -1;
     Vec<VEC> gi;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
-    for (int t = 0; t < per; ++t) {
-        const int64_t e = e_begin + t;
-        const bool active = e < n_kept;
-        int32_t p = 0, i = 0;
-        uint32_t t_idx[NP];
-        float sc_a = 0.f, sc_r = 0.f;
-        t_idx[0] = 0;
-        if (active) {
-            p = kept_pos[e];
-            i = row[p];
-            t_idx[0] = (uint32_t)col[p];
-            const float kb = (float)batch_kept[i / batch_size];
-            sc_a = inv_nb / kb;
-            sc_r = inv_nb / (kb * (float)R);
-            if (i != cur_i) {                                     // group-uniform: the lanes of a group share e
-                if (cur_i >= 0) red_vec<VEC>(grad_head + (int64_t)cur_i * DIM + gl * VEC, gi, 1.0f);
+    for (int round = 0, buf = 0; round < n_rounds; ++round, buf ^= 1) {
+        if (round + 1 < n_rounds) { issue(buf ^ 1, round + 1); cp_async_wait_group<1>(); }
+        else cp_async_wait_group<0>();
+        __syncthreads();
+        const int64_t e_begin = blk_lo + (int64_t)round * per_round + (int64_t)grp * tr;
+        for (int t = 0; t < tr; ++t) {
+            const int64_t e = e_begin + t;
+            const bool active = e < blk_hi;
+            int32_t p = 0, i = 0;
+            uint32_t t_idx[NP];
+            float sc_a = 0.f, sc_r = 0.f;
+            t_idx[0] = 0;
+            if (active) {
+                const int4 rec = s_rec[buf][grp * STRIDE + t];
+                p = rec.x;
+                i = rec.y;
+                t_idx[0] = (uint32_t)rec.z;
+                const float kb = (float)batch_kept[rec.w];
+                sc_a = inv_nb / kb;
+                sc_r = inv_nb / (kb * (float)R);
+                if (i != cur_i) {                                     // group-uniform: the lanes of a group share e
+                    if (cur_i >= 0) red_vec<VEC>(grad_head + (int64_t)cur_i * DIM + gl * VEC, gi, 1.0f);
 #pragma unroll
-                for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
-                cur_i = i;
+                    for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
+                    cur_i = i;
+                }
+            }
+            if (neg) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) t_idx[r + 1] = active ? (uint32_t)neg[e * R + r] : 0u;
+            } else if (LANES >= NCALL) {
+                // lane c of the group evaluates call c (same counters as the loop version: identical draws)
+                const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)(gl % NCALL), epoch, STREAM_NEG, k0, k1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t mine_w = (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w;
+                    t_idx[r + 1] = urange(__shfl_sync(0xffffffffu, mine_w, r >> 2, LANES), rep_count);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NCALL; ++c) {
+                    const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)c, epoch, STREAM_NEG, k0, k1);
+                    if (4 * c + 0 < R) t_idx[4 * c + 1] = urange(w.x, rep_count);
+                    if (4 * c + 1 < R) t_idx[4 * c + 2] = urange(w.y, rep_count);
+                    if (4 * c + 2 < R) t_idx[4 * c + 3] = urange(w.z, rep_count);
+                    if (4 * c + 3 < R) t_idx[4 * c + 4] = urange(w.w, rep_count);
+                }
+            }
+            // which pairs this launch handles (all of them without windows)
+            bool inw[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) inw[q] = active && (!WIN || (t_idx[q] - win_lo) < win_len);
+            // gather: head row + the tail rows, then differences and squared distances
+            const Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * DIM + gl * VEC);
+            Vec<VEC> df[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if (WIN) {
+                    if (inw[q]) df[q] = load_vec_cg<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) df[q].v[c] = 0.f;
+                    }
+                } else {
+                    df[q] = load_vec<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
+                }
+            }
+            float s[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) { df[q].v[c] = yi.v[c] - df[q].v[c]; acc = fmaf(df[q].v[c], df[q].v[c], acc); }
+                s[q] = group_sum<LANES>(acc);
+            }
+            // coefficients: pair q is evaluated by lane q % LANES
+            float cv[ROUNDS];
+#pragma unroll
+            for (int u0 = 0; u0 < ROUNDS; ++u0) {
+                float sv = 1.0f;
+                bool valid = false;
+#pragma unroll
+                for (int u = 0; u < LANES; ++u)
+                    if (u0 * LANES + u < NP && gl == u) { sv = s[u0 * LANES + u]; valid = inw[u0 * LANES + u]; }
+                float l = 0.f;
+                const float cf = pair_coef<FAST>(sv, u0 == 0 && gl == 0, a, b, sc_a, sc_r, want_loss, l);
+                cv[u0] = valid ? cf : 0.f;
+                if (want_loss && valid) loss_acc += l;
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const float coef = LANES == 1 ? cv[q] : __shfl_sync(0xffffffffu, cv[q / LANES], q % LANES, LANES);
+                Vec<VEC> g;
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df[q].v[c]; gi.v[c] += g.v[c]; }
+                if (inw[q] && grad_tail) red_vec<VEC>(grad_tail + (int64_t)t_idx[q] * DIM + gl * VEC, g, -1.0f);
             }
         }
-        if (neg) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) t_idx[r + 1] = active ? (uint32_t)neg[e * R + r] : 0u;
-        } else if (LANES >= NCALL) {
-            const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)(gl % NCALL), epoch, STREAM_NEG, k0, k1);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t mine = (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w;
-                t_idx[r + 1] = urange(__shfl_sync(0xffffffffu, mine, r >> 2, LANES), rep_count);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCALL; ++c) {
-                const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)c, epoch, STREAM_NEG, k0, k1);
-                if (4 * c + 0 < R) t_idx[4 * c + 1] = urange(w.x, rep_count);
-                if (4 * c + 1 < R) t_idx[4 * c + 2] = urange(w.y, rep_count);
-                if (4 * c + 2 < R) t_idx[4 * c + 3] = urange(w.z, rep_count);
-                if (4 * c + 3 < R) t_idx[4 * c + 4] = urange(w.w, rep_count);
-            }
-        }
-        const Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * DIM + gl * VEC);
-        Vec<VEC> df[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) df[q] = load_vec<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
-        float s[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) { df[q].v[c] = yi.v[c] - df[q].v[c]; acc = fmaf(df[q].v[c], df[q].v[c], acc); }
-            s[q] = group_sum<LANES>(acc);
-        }
-        float cv[ROUNDS];
-#pragma unroll
-        for (int u0 = 0; u0 < ROUNDS; ++u0) {
-            float sv = 1.0f;
-            bool valid = false;
-#pragma unroll
-            for (int u = 0; u < LANES; ++u)
-                if (u0 * LANES + u < NP && gl == u) { sv = s[u0 * LANES + u]; valid = true; }
-            float l = 0.f;
-            const float cf = pair_coef<FAST>(sv, u0 == 0 && gl == 0, a, b, sc_a, sc_r, want_loss, l);
-            cv[u0] = (valid && active) ? cf : 0.f;
-            if (want_loss && valid && active) loss_acc += l;
-        }
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const float coef = LANES == 1 ? cv[q] : __shfl_sync(0xffffffffu, cv[q / LANES], q % LANES, LANES);
-            Vec<VEC> g;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df[q].v[c]; gi.v[c] += g.v[c]; }
-            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)t_idx[q] * DIM + gl * VEC, g, -1.0f);
-        }
+        __syncthreads();                                              // the buffer is refilled two rounds later
     }
     if (cur_i >= 0) red_vec<VEC>(grad_head + (int64_t)cur_i * DIM + gl * VEC, gi, 1.0f);
     if (want_loss) {
@@ -397,136 +482,15 @@ edge_forces_runs_kernel(const int32_t *__restrict__ row, const int32_t *__restri
     }
 }
 
-template <int VEC, int LANES, int R, bool FAST, bool REC>
-__global__ void __launch_bounds__(256, 3)
-edge_forces_rb_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                      const int32_t *__restrict__ kept_pos, const int4 *__restrict__ kept_rec,
-                      const int32_t *__restrict__ kept_count,
-                      const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
-                      int batch_size, uint32_t rep_count, const float *__restrict__ head,
-                      const float *__restrict__ tail, float *__restrict__ grad_head, float *__restrict__ grad_tail,
-                      float a, float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
-    constexpr int DIM = VEC * LANES;
-    constexpr int NP = R + 1;                                 // pairs per kept edge: 1 attractive + R repulsive
-    constexpr int NCALL = (R + 3) / 4;                        // Philox calls per edge
-    constexpr int ROUNDS = (NP + LANES - 1) / LANES;
-    const int n_kept = *kept_count;
-    const uint32_t epoch = st->epoch;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const int gl = threadIdx.x % LANES;
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-    const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-    const float inv_nb = 1.0f / (float)n_batches;
-    const bool want_loss = loss_out != nullptr;
-    float loss_acc = 0.f;
-    constexpr int64_t gpw = 32 / LANES;
-    const int64_t wfirst = (gid / gpw) * gpw;
-    // REC: the kept-edge record of the NEXT iteration is fetched while this one is processed
-    int4 rec_next = make_int4(0, 0, 0, 0);
-    if (REC && wfirst + (gid - wfirst) < n_kept) rec_next = kept_rec[wfirst + (gid - wfirst)];
-    for (int64_t e0 = wfirst; e0 < n_kept; e0 += n_groups) {
-        const int64_t e = e0 + (gid - wfirst);
-        const bool active = e < n_kept;
-        int32_t p = 0, i = 0;
-        uint32_t t_idx[NP];
-        float sc_a = 0.f, sc_r = 0.f;
-        t_idx[0] = 0;
-        if (REC) {
-            const int4 rec = rec_next;
-            if (e + n_groups < n_kept) rec_next = kept_rec[e + n_groups];
-            if (active) {
-                p = rec.x;
-                i = rec.y;
-                t_idx[0] = (uint32_t)rec.z;
-                const float kb = (float)batch_kept[rec.w];
-                sc_a = inv_nb / kb;
-                sc_r = inv_nb / (kb * (float)R);
-            }
-        } else if (active) {
-            p = kept_pos[e];
-            i = row[p];
-            t_idx[0] = (uint32_t)col[p];
-            const float kb = (float)batch_kept[i / batch_size];
-            sc_a = inv_nb / kb;
-            sc_r = inv_nb / (kb * (float)R);
-        }
-        if (neg) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) t_idx[r + 1] = active ? (uint32_t)neg[e * R + r] : 0u;
-        } else if (LANES >= NCALL) {
-            // lane c of the group evaluates call c (same counters as the loop version: identical draws)
-            const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)(gl % NCALL), epoch, STREAM_NEG, k0, k1);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t mine = (r & 3) == 0 ? w.x : (r & 3) == 1 ? w.y : (r & 3) == 2 ? w.z : w.w;
-                t_idx[r + 1] = urange(__shfl_sync(0xffffffffu, mine, r >> 2, LANES), rep_count);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCALL; ++c) {
-                const Philox4 w = philox4x32_10((uint32_t)p, (uint32_t)c, epoch, STREAM_NEG, k0, k1);
-                if (4 * c + 0 < R) t_idx[4 * c + 1] = urange(w.x, rep_count);
-                if (4 * c + 1 < R) t_idx[4 * c + 2] = urange(w.y, rep_count);
-                if (4 * c + 2 < R) t_idx[4 * c + 3] = urange(w.z, rep_count);
-                if (4 * c + 3 < R) t_idx[4 * c + 4] = urange(w.w, rep_count);
-            }
-        }
-        // gather: head row + all tail rows, then differences and squared distances
-        const Vec<VEC> yi = load_vec<VEC>(head + (int64_t)i * DIM + gl * VEC);
-        Vec<VEC> df[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) df[q] = load_vec<VEC>(tail + (int64_t)t_idx[q] * DIM + gl * VEC);
-        float s[NP];
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) { df[q].v[c] = yi.v[c] - df[q].v[c]; acc = fmaf(df[q].v[c], df[q].v[c], acc); }
-            s[q] = group_sum<LANES>(acc);
-        }
-        // coefficients: pair q is evaluated by lane q % LANES
-        float cv[ROUNDS];
-#pragma unroll
-        for (int t = 0; t < ROUNDS; ++t) {
-            float sv = 1.0f;
-            bool valid = false;
-#pragma unroll
-            for (int u = 0; u < LANES; ++u)
-                if (t * LANES + u < NP && gl == u) { sv = s[t * LANES + u]; valid = true; }
-            float l = 0.f;
-            const float cf = pair_coef<FAST>(sv, t == 0 && gl == 0, a, b, sc_a, sc_r, want_loss, l);
-            cv[t] = valid ? cf : 0.f;
-            if (want_loss && valid) loss_acc += l;
-        }
-        Vec<VEC> gi;
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) gi.v[c] = 0.f;
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            const float coef = LANES == 1 ? cv[q] : __shfl_sync(0xffffffffu, cv[q / LANES], q % LANES, LANES);
-            Vec<VEC> g;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) { g.v[c] = coef * df[q].v[c]; gi.v[c] += g.v[c]; }
-            if (active && grad_tail) red_vec<VEC>(grad_tail + (int64_t)t_idx[q] * DIM + gl * VEC, g, -1.0f);
-        }
-        if (active) red_vec<VEC>(grad_head + (int64_t)i * DIM + gl * VEC, gi, 1.0f);
-    }
-    if (want_loss) {
-        loss_acc = warp_sum(loss_acc);
-        if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
-    }
-}
-
 // generic dimension: one warp per kept edge, lane owns components lane, lane+32, ... (dim <= 128)
 __global__ void __launch_bounds__(256)
-edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                           const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+edge_forces_generic_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict__ kept_hdr,
                            const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept,
-                           int n_batches, int batch_size, int num_rep, uint32_t rep_count,
+                           int n_batches, int num_rep, uint32_t rep_count,
                            const float *__restrict__ head, const float *__restrict__ tail,
                            float *__restrict__ grad_head, float *__restrict__ grad_tail, int dim, float a,
                            float b, uint64_t seed, const OptState *__restrict__ st, float *__restrict__ loss_out) {
-    const int n_kept = *kept_count;
+    const int n_kept = kept_total(kept_hdr);
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31;
@@ -535,9 +499,9 @@ edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__res
     const float inv_nb = 1.0f / (float)n_batches;
     float loss_acc = 0.f;
     for (int64_t e = wid; e < n_kept; e += n_warps) {
-        int32_t p = kept_pos[e];
-        int32_t i = row[p], j = col[p];
-        float kb = (float)batch_kept[i / batch_size];
+        const int4 rec = kept_rec[e];
+        const int32_t p = rec.x, i = rec.y, j = rec.z;
+        float kb = (float)batch_kept[rec.w];
         float sc_a = inv_nb / kb, sc_r = inv_nb / (kb * (float)num_rep);
         float yi[4], gi[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -583,41 +547,44 @@ edge_forces_generic_kernel(const int32_t *__restrict__ row, const int32_t *__res
 // ref: model.py:336-362 (_inv_attr_loss, _inv_rep_loss) as used by _train in mode "invert"
 // (model.py:437,447).  The variable is a Q x D table in DATA space (D up to thousands), the tails
 // are rows of the fitted modality's data with their fit-time sigma / rho.  One warp per kept edge:
-// phase 1 computes the 1+R squared distances (lane-strided, coalesced), phase 2 forms
-// sum_p coef_p (x - y_p) per component and issues ONE red per component.
+// phase 1 computes the 1+R squared distances with all 1+R tail rows streamed together (float4 per lane when
+// D % 4 == 0: 1+R independent 16-byte loads in flight per lane), phase 2 forms sum_p coef_p (x - y_p) per
+// component -- the rows are L1/L2 hits now -- and issues ONE red per component (vector red when D % 4 == 0).
 constexpr int INV_MAXP = 17;      // 1 attractive + up to 16 repulsive pairs
 
+template <int NPT>                // compile-time pair count (1 + num_rep) or 0 = run-time (<= INV_MAXP)
 __global__ void __launch_bounds__(256)
-invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
-                     const int32_t *__restrict__ kept_pos, const int32_t *__restrict__ kept_count,
+invert_forces_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict__ kept_hdr,
                      const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
-                     int batch_size, int num_rep, uint32_t rep_count, const float *__restrict__ head,
+                     int num_rep, uint32_t rep_count, const float *__restrict__ head,
                      const float *__restrict__ data, const float *__restrict__ sigma, const float *__restrict__ rho,
                      float *__restrict__ grad_head, int dim, float a, float b, uint64_t seed,
                      const OptState *__restrict__ st, float *__restrict__ loss_out) {
-    const int n_kept = *kept_count;
+    constexpr int MAXP = NPT ? NPT : INV_MAXP;
+    const int n_kept = kept_total(kept_hdr);
     const uint32_t epoch = st->epoch;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv_nb = 1.0f / (float)n_batches;
-    const int np = 1 + num_rep;
+    const int np = NPT ? NPT : 1 + num_rep;
+    const bool vec4 = (dim & 3) == 0;
     float loss_acc = 0.f;
     for (int64_t e = wid; e < n_kept; e += n_warps) {
-        const int32_t p = kept_pos[e];
-        const int32_t i = row[p];
-        const float kb = (float)batch_kept[i / batch_size];
+        const int4 rec = kept_rec[e];
+        const int32_t p = rec.x, i = rec.y;
+        const float kb = (float)batch_kept[rec.w];
         const float sc_a = inv_nb / kb, sc_r = inv_nb / (kb * (float)num_rep);
         const float *xi = head + (int64_t)i * dim;
-        uint32_t t_idx[INV_MAXP];
-        float coef[INV_MAXP];
+        uint32_t t_idx[MAXP];
+        float coef[MAXP], s_raw[MAXP];
         Philox4 rnd = {0, 0, 0, 0};
 #pragma unroll
-        for (int q = 0; q < INV_MAXP; ++q) {
-            t_idx[q] = 0; coef[q] = 0.f;
+        for (int q = 0; q < MAXP; ++q) {
+            t_idx[q] = 0; coef[q] = 0.f; s_raw[q] = 0.f;
             if (q >= np) continue;
-            if (q == 0) t_idx[q] = (uint32_t)col[p];
+            if (q == 0) t_idx[q] = (uint32_t)rec.z;
             else if (neg) t_idx[q] = (uint32_t)neg[e * num_rep + (q - 1)];
             else {
                 const int r = q - 1;
@@ -625,11 +592,38 @@ invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict_
                 const uint32_t x = (r & 3) == 0 ? rnd.x : (r & 3) == 1 ? rnd.y : (r & 3) == 2 ? rnd.z : rnd.w;
                 t_idx[q] = urange(x, rep_count);
             }
-            const float *yt = data + (int64_t)t_idx[q] * dim;
-            float s_raw = 0.f;
-            for (int c = lane; c < dim; c += 32) { const float df = xi[c] - yt[c]; s_raw = fmaf(df, df, s_raw); }
-            s_raw = warp_sum(s_raw);
-            const float s = fmaxf(s_raw, 1e-6f);
+        }
+        // phase 1: squared distances; per-pair accumulation order = components ascending within a lane, then the
+        // warp tree -- the same for the scalar and the float4 layout of the lane's components is NOT required
+        // (the test tolerance is relative 1e-4), so each path uses its natural order
+        if (vec4) {
+            for (int c = lane * 4; c < dim; c += 128) {
+                const float4 x = *reinterpret_cast<const float4 *>(xi + c);
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    if (q >= np) continue;
+                    const float4 y = __ldg(reinterpret_cast<const float4 *>(data + (int64_t)t_idx[q] * dim + c));
+                    float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+                    s_raw[q] = fmaf(d0, d0, s_raw[q]); s_raw[q] = fmaf(d1, d1, s_raw[q]);
+                    s_raw[q] = fmaf(d2, d2, s_raw[q]); s_raw[q] = fmaf(d3, d3, s_raw[q]);
+                }
+            }
+        } else {
+            for (int c = lane; c < dim; c += 32) {
+                const float x = xi[c];
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    if (q >= np) continue;
+                    const float df = x - data[(int64_t)t_idx[q] * dim + c];
+                    s_raw[q] = fmaf(df, df, s_raw[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MAXP; ++q) {
+            if (q >= np) continue;
+            const float sr = warp_sum(s_raw[q]);
+            const float s = fmaxf(sr, 1e-6f);
             const float dist = sqrtf(s);
             const float sg = sigma[t_idx[q]];
             float dls, l;
@@ -646,16 +640,32 @@ invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict_
                 l = -sc_r * logf(om);
                 dls = (c_raw >= 1e-6f) ? sc_r * (-ex / (sg + 1e-6f)) / (om * 2.0f * dist) : 0.f;
             }
-            coef[q] = (s_raw >= 1e-6f) ? 2.0f * dls : 0.f;
+            coef[q] = (sr >= 1e-6f) ? 2.0f * dls : 0.f;
             if (lane == 0) loss_acc += l;
         }
-        for (int c = lane; c < dim; c += 32) {
-            const float x = xi[c];
-            float g = 0.f;
+        // phase 2
+        if (vec4) {
+            for (int c = lane * 4; c < dim; c += 128) {
+                const float4 x = *reinterpret_cast<const float4 *>(xi + c);
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
 #pragma unroll
-            for (int q = 0; q < INV_MAXP; ++q)
-                if (q < np) g = fmaf(coef[q], x - data[(int64_t)t_idx[q] * dim + c], g);
-            red_add_f32(grad_head + (int64_t)i * dim + c, g);
+                for (int q = 0; q < MAXP; ++q) {
+                    if (q >= np) continue;
+                    const float4 y = __ldg(reinterpret_cast<const float4 *>(data + (int64_t)t_idx[q] * dim + c));
+                    g0 = fmaf(coef[q], x.x - y.x, g0); g1 = fmaf(coef[q], x.y - y.y, g1);
+                    g2 = fmaf(coef[q], x.z - y.z, g2); g3 = fmaf(coef[q], x.w - y.w, g3);
+                }
+                red_add_v4(grad_head + (int64_t)i * dim + c, g0, g1, g2, g3);
+            }
+        } else {
+            for (int c = lane; c < dim; c += 32) {
+                const float x = xi[c];
+                float g = 0.f;
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q)
+                    if (q < np) g = fmaf(coef[q], x - data[(int64_t)t_idx[q] * dim + c], g);
+                red_add_f32(grad_head + (int64_t)i * dim + c, g);
+            }
         }
     }
     if (loss_out && lane == 0 && loss_acc != 0.f) atomicAdd(loss_out, loss_acc);
@@ -663,6 +673,19 @@ invert_forces_kernel(const int32_t *__restrict__ row, const int32_t *__restrict_
 
 // ------------------------------------------------------------------ K8: InfoNCE
 constexpr int NCE_MAX = 16;   // 1 positive + up to 15 negatives
+
+// Device sample stream: the reference re-draws randperm(num) every epoch (model.py:373), so which anchors fall into
+// the short last chunk (and get the larger per-anchor weight 1/(clen*n_chunks), model.py:392-394) changes from epoch
+// to epoch.  The device stream keeps position order but rotates it by a per-epoch, per-direction random offset:
+// anchor position t holds row (t + offset) mod num, so the short chunk is a different row range every epoch and all
+// rows are weighted equally in expectation.  (The host stream uploads the reference's own permutation instead.)
+__device__ __forceinline__ int32_t nce_rotated_anchor(int64_t t, int64_t num, uint32_t epoch, uint32_t stream_id, uint64_t seed) {
+    const Philox4 r = philox4x32_10(0xffffffffu, 0xffffffffu, epoch, STREAM_INFONCE + stream_id, (uint32_t)seed,
+                                    (uint32_t)(seed >> 32));
+    const int64_t off = (int64_t)urange(r.x, (uint32_t)num);
+    const int64_t v = t + off;
+    return (int32_t)(v >= num ? v - num : v);
+}
 
 __global__ void __launch_bounds__(128)
 infonce_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_, int64_t num, int64_t a_lo, int64_t a_hi, int dim,
@@ -685,7 +708,7 @@ infonce_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_, int
         const int64_t cidx = t / chunk;
         const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
         const float wgt = weight / ((float)clen * (float)n_chunks);       // ref: model.py:392,394
-        const int32_t i = perm ? perm[t] : (int32_t)t;
+        const int32_t i = perm ? perm[t] : nce_rotated_anchor(t, num, st->epoch, stream_id, seed);
         const int M = 1 + n_neg;
         int32_t ids[NCE_MAX];
         bool ok[NCE_MAX];
@@ -782,7 +805,7 @@ infonce_vec_kernel(const float *__restrict__ e0_, const float *__restrict__ e1_,
     const int64_t cidx = tt / chunk;
     const int64_t clen = min((int64_t)chunk, num - cidx * chunk);
     const float wgt = weight / ((float)clen * (float)n_chunks);           // ref: model.py:392,394
-    const int32_t i = perm ? perm[tt] : (int32_t)tt;
+    const int32_t i = perm ? perm[tt] : nce_rotated_anchor(tt, num, st->epoch, stream_id, seed);
     const int M = MT ? MT : 1 + n_neg;
     constexpr int MCAP = MT ? MT : NCE_MAX;
     int32_t ids[MCAP];
@@ -952,206 +975,162 @@ extern "C" int mmu_opt_state_advance(uint32_t *state, double lr, double beta1, d
     return MMU_OK;
 }
 
-extern "C" int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi, int batch_size,
-                                  int n_batches, uint64_t seed, int64_t epoch, const uint32_t *state, int32_t *kept_pos,
-                                  int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream);
-
-extern "C" int mmu_edge_sample_range(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi,
-                                     int batch_size, int n_batches, uint64_t seed, const uint32_t *state,
-                                     int32_t *kept_pos, int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream) {
-    return mmu_edge_sample_at(row, w, edge_lo, edge_hi, batch_size, n_batches, seed, -1, state, kept_pos, kept_count,
-                              batch_kept, stream);
-}
-
-extern "C" int mmu_edge_sample_at(const int32_t *row, const float *w, int64_t edge_lo, int64_t edge_hi, int batch_size,
-                                  int n_batches, uint64_t seed, int64_t epoch, const uint32_t *state, int32_t *kept_pos,
-                                  int32_t *kept_count, int32_t *batch_kept, mmu_stream_t stream) {
+extern "C" int mmu_edge_sample_at(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                                  int64_t edge_hi, int batch_size, int n_batches, uint64_t seed, int64_t epoch,
+                                  const uint32_t *state, int32_t *kept_rec, int32_t *kept_hdr, int32_t *batch_kept,
+                                  mmu_stream_t stream) {
     using namespace mmu;
-    MMU_CHECK_ARG(row && w && state && kept_pos && kept_count && batch_kept, "mmu_edge_sample: null pointer");
+    MMU_CHECK_ARG(row && col && w && state && kept_rec && kept_hdr && batch_kept, "mmu_edge_sample: null pointer");
+    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(kept_rec) & 15) == 0, "mmu_edge_sample: kept_rec must be 16-byte aligned");
     MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample: bad batch geometry");
     MMU_CHECK_ARG(edge_lo >= 0 && edge_hi >= edge_lo && edge_hi < ((int64_t)1 << 31), "mmu_edge_sample: bad edge range");
     cudaStream_t st = as_stream(stream);
-    MMU_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st));
+    MMU_CUDA(cudaMemsetAsync(kept_hdr, 0, sizeof(int32_t), st));            // the count; capacity and flag stay
     MMU_CUDA(cudaMemsetAsync(batch_kept, 0, sizeof(int32_t) * (size_t)n_batches, st));
     if (edge_hi == edge_lo) return MMU_OK;
     int64_t n4 = (edge_hi + 3) / 4 - edge_lo / 4;
     int64_t want = (n4 + 255) / 256;
     unsigned cap = persistent_blocks(256, 8);
     unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
-    edge_sample_kernel<false><<<blocks, 256, 0, st>>>(row, nullptr, w, edge_lo, edge_hi, batch_size, seed,
-                                                      reinterpret_cast<const OptState *>(state), kept_pos, nullptr,
-                                                      kept_count, batch_kept, epoch);
+    edge_sample_kernel<<<blocks, 256, 0, st>>>(row, col, w, edge_lo, edge_hi, batch_size, seed,
+                                               reinterpret_cast<const OptState *>(state),
+                                               reinterpret_cast<int4 *>(kept_rec), kept_hdr, batch_kept, epoch);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
 
-extern "C" int mmu_edge_sample_records(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
-                                       int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
-                                       const uint32_t *state, int32_t *kept_rec, int32_t *kept_count,
-                                       int32_t *batch_kept, mmu_stream_t stream) {
+extern "C" int mmu_edge_sample_range(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
+                                     int64_t edge_hi, int batch_size, int n_batches, uint64_t seed,
+                                     const uint32_t *state, int32_t *kept_rec, int32_t *kept_hdr, int32_t *batch_kept,
+                                     mmu_stream_t stream) {
+    return mmu_edge_sample_at(row, col, w, edge_lo, edge_hi, batch_size, n_batches, seed, -1, state, kept_rec, kept_hdr,
+                              batch_kept, stream);
+}
+
+extern "C" int mmu_edge_records(const int32_t *row, const int32_t *col, const int32_t *kept_pos, int64_t n_kept,
+                                int batch_size, int32_t *kept_rec, int32_t *kept_hdr, mmu_stream_t stream) {
     using namespace mmu;
-    MMU_CHECK_ARG(row && col && w && state && kept_rec && kept_count && batch_kept, "mmu_edge_sample_records: null pointer");
-    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(kept_rec) & 15) == 0, "mmu_edge_sample_records: kept_rec must be 16-byte aligned");
-    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_sample_records: bad batch geometry");
-    MMU_CHECK_ARG(edge_lo >= 0 && edge_hi >= edge_lo && edge_hi < ((int64_t)1 << 31), "mmu_edge_sample_records: bad edge range");
-    cudaStream_t st = as_stream(stream);
-    MMU_CUDA(cudaMemsetAsync(kept_count, 0, sizeof(int32_t), st));
-    MMU_CUDA(cudaMemsetAsync(batch_kept, 0, sizeof(int32_t) * (size_t)n_batches, st));
-    if (edge_hi == edge_lo) return MMU_OK;
-    int64_t n4 = (edge_hi + 3) / 4 - edge_lo / 4;
-    int64_t want = (n4 + 255) / 256;
-    unsigned cap = persistent_blocks(256, 8);
-    unsigned blocks = (unsigned)(want < (int64_t)cap ? want : cap);
-    edge_sample_kernel<true><<<blocks, 256, 0, st>>>(row, col, w, edge_lo, edge_hi, batch_size, seed,
-                                                     reinterpret_cast<const OptState *>(state), nullptr,
-                                                     reinterpret_cast<int4 *>(kept_rec), kept_count, batch_kept, -1);
+    MMU_CHECK_ARG(row && col && kept_pos && kept_rec && kept_hdr, "mmu_edge_records: null pointer");
+    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(kept_rec) & 15) == 0, "mmu_edge_records: kept_rec must be 16-byte aligned");
+    MMU_CHECK_ARG(n_kept >= 0 && n_kept < ((int64_t)1 << 31) && batch_size >= 1, "mmu_edge_records: bad sizes");
+    const unsigned blocks = (unsigned)((n_kept + 255) / 256 > 0 ? (n_kept + 255) / 256 : 1);
+    edge_records_kernel<<<blocks, 256, 0, as_stream(stream)>>>(row, col, kept_pos, n_kept, batch_size,
+                                                               reinterpret_cast<int4 *>(kept_rec), kept_hdr);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
 
-extern "C" int mmu_edge_sample(const int32_t *row, const float *w, int64_t nnz, int batch_size, int n_batches,
-                               uint64_t seed, const uint32_t *state, int32_t *kept_pos, int32_t *kept_count,
-                               int32_t *batch_kept, mmu_stream_t stream) {
-    return mmu_edge_sample_range(row, w, 0, nnz, batch_size, n_batches, seed, state, kept_pos, kept_count, batch_kept,
-                                 stream);
-}
-
-extern "C" int mmu_edge_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
-                               const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept,
-                               int n_batches, int batch_size, int num_rep, int64_t rep_count, const float *head,
-                               const float *tail, float *grad_head, float *grad_tail, int dim, float a, float b,
-                               uint64_t seed, const uint32_t *state, float *loss, int fast_math, mmu_stream_t stream) {
+extern "C" int mmu_edge_forces(const int32_t *kept_rec, const int32_t *kept_hdr, const int32_t *neg,
+                               const int32_t *batch_kept, int n_batches, int num_rep, int64_t rep_count,
+                               const float *head, const float *tail, float *grad_head, float *grad_tail, int dim,
+                               float a, float b, uint64_t seed, const uint32_t *state, float *loss, int fast_math,
+                               int64_t window_rows, mmu_stream_t stream) {
     using namespace mmu;
-    MMU_CHECK_ARG(row && col && kept_pos && kept_count && batch_kept && head && tail && grad_head && state,
-                  "mmu_edge_forces: null pointer");
+    MMU_CHECK_ARG(kept_rec && kept_hdr && batch_kept && head && tail && grad_head && state, "mmu_edge_forces: null pointer");
+    MMU_CHECK_ARG((reinterpret_cast<uintptr_t>(kept_rec) & 15) == 0, "mmu_edge_forces: kept_rec must be 16-byte aligned");
     MMU_CHECK_ARG(dim >= 1 && dim <= 128, "mmu_edge_forces: dim=%d outside [1,128]", dim);
     MMU_CHECK_ARG(num_rep >= 0 && rep_count >= 1 && rep_count < ((int64_t)1 << 31), "mmu_edge_forces: bad negatives");
-    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_edge_forces: bad batch geometry");
-    cudaStream_t st = as_stream(stream);
-    const OptState *os = reinterpret_cast<const OptState *>(state);
-    unsigned blocks = persistent_blocks(256, 8);
-    // run form (head gradient accumulated per run of equal rows) unless MMUMAP_FORCE_RUNS=0
-    const char *runs_env = getenv("MMUMAP_FORCE_RUNS");
-    const bool runs = !(runs_env && runs_env[0] == '0');
-    // the register-blocked kernels hold 3 blocks per SM (__launch_bounds__(256, 3)): a grid of whole waves
-    // (measured per epoch on C2: 3/SM 279.9 us, 6/SM 284.3, 8/SM 289.4, 9/SM 279.9, 12/SM 291.1)
-    const unsigned blocks_generic = blocks;
-    if (num_rep == 8 || num_rep == 4) blocks = persistent_blocks(256, 3);
-#define MMU_FORCES(V, L)                                                                                        \
-    edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept, n_batches, \
-                                                     batch_size, num_rep, (uint32_t)rep_count, head, tail,       \
-                                                     grad_head, grad_tail, dim, a, b, seed, os, loss)
-#define MMU_FORCES_RB(V, L, RR)                                                                                  \
-    do {                                                                                                         \
-        if (runs && fast_math)                                                                                   \
-            edge_forces_runs_kernel<V, L, RR, true><<<blocks, 256, 0, st>>>(                                     \
-                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size,                          \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-        else if (runs)                                                                                           \
-            edge_forces_runs_kernel<V, L, RR, false><<<blocks, 256, 0, st>>>(                                    \
-                row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size,                          \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-        else if (fast_math)                                                                                      \
-            edge_forces_rb_kernel<V, L, RR, true, false><<<blocks, 256, 0, st>>>(                                \
-                row, col, kept_pos, nullptr, kept_count, neg, batch_kept, n_batches, batch_size,                 \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-        else                                                                                                     \
-            edge_forces_rb_kernel<V, L, RR, false, false><<<blocks, 256, 0, st>>>(                               \
-                row, col, kept_pos, nullptr, kept_count, neg, batch_kept, n_batches, batch_size,                 \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-    } while (0)
-#define MMU_FORCES_DIM(V, L)                                      \
-    do {                                                          \
-        if (num_rep == 8) MMU_FORCES_RB(V, L, 8);                 \
-        else if (num_rep == 4) MMU_FORCES_RB(V, L, 4);            \
-        else MMU_FORCES(V, L);                                    \
-    } while (0)
-    switch (dim) {
-        case 2: MMU_FORCES_DIM(2, 1); break;
-        case 4: MMU_FORCES_DIM(4, 1); break;
-        case 8: MMU_FORCES_DIM(4, 2); break;
-        case 16: MMU_FORCES_DIM(4, 4); break;
-        case 32: MMU_FORCES_DIM(4, 8); break;
-        case 64: MMU_FORCES_DIM(4, 16); break;
-        case 128: MMU_FORCES_DIM(4, 32); break;
-        default:
-            edge_forces_generic_kernel<<<blocks_generic, 256, 0, st>>>(row, col, kept_pos, kept_count, neg, batch_kept,
-                                                               n_batches, batch_size, num_rep, (uint32_t)rep_count,
-                                                               head, tail, grad_head, grad_tail, dim, a, b, seed, os, loss);
-    }
-#undef MMU_FORCES_DIM
-#undef MMU_FORCES_RB
-#undef MMU_FORCES
-    MMU_LAUNCH_CHECK();
-    return MMU_OK;
-}
-
-extern "C" int mmu_edge_forces_records_supported(int dim, int num_rep) {
-    const bool d = dim == 2 || dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128;
-    return (d && (num_rep == 8 || num_rep == 4)) ? 1 : 0;
-}
-
-extern "C" int mmu_edge_forces_records(const int32_t *kept_rec, const int32_t *kept_count, const int32_t *batch_kept,
-                                       int n_batches, int num_rep, int64_t rep_count, const float *head,
-                                       const float *tail, float *grad_head, float *grad_tail, int dim, float a, float b,
-                                       uint64_t seed, const uint32_t *state, float *loss, int fast_math,
-                                       mmu_stream_t stream) {
-    using namespace mmu;
-    MMU_CHECK_ARG(kept_rec && kept_count && batch_kept && head && tail && grad_head && state,
-                  "mmu_edge_forces_records: null pointer");
-    MMU_CHECK_ARG(mmu_edge_forces_records_supported(dim, num_rep), "mmu_edge_forces_records: unsupported dim=%d / num_rep=%d",
-                  dim, num_rep);
-    MMU_CHECK_ARG(rep_count >= 1 && rep_count < ((int64_t)1 << 31) && n_batches >= 1, "mmu_edge_forces_records: bad sizes");
+    MMU_CHECK_ARG(n_batches >= 1 && window_rows >= 0, "mmu_edge_forces: bad batch geometry / window");
     cudaStream_t st = as_stream(stream);
     const OptState *os = reinterpret_cast<const OptState *>(state);
     const int4 *rec = reinterpret_cast<const int4 *>(kept_rec);
-    unsigned blocks = persistent_blocks(256, 3);      // whole waves at 3 blocks per SM
-#define MMU_FREC(V, L, RR)                                                                                       \
-    do {                                                                                                         \
-        if (fast_math)                                                                                           \
-            edge_forces_rb_kernel<V, L, RR, true, true><<<blocks, 256, 0, st>>>(                                 \
-                nullptr, nullptr, nullptr, rec, kept_count, nullptr, batch_kept, n_batches, 1,                   \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-        else                                                                                                     \
-            edge_forces_rb_kernel<V, L, RR, false, true><<<blocks, 256, 0, st>>>(                                \
-                nullptr, nullptr, nullptr, rec, kept_count, nullptr, batch_kept, n_batches, 1,                   \
-                (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b, seed, os, loss);                    \
-    } while (0)
-#define MMU_FREC_DIM(V, L)                       \
-    do {                                         \
-        if (num_rep == 8) MMU_FREC(V, L, 8);     \
-        else MMU_FREC(V, L, 4);                  \
-    } while (0)
-    switch (dim) {
-        case 2: MMU_FREC_DIM(2, 1); break;
-        case 4: MMU_FREC_DIM(4, 1); break;
-        case 8: MMU_FREC_DIM(4, 2); break;
-        case 16: MMU_FREC_DIM(4, 4); break;
-        case 32: MMU_FREC_DIM(4, 8); break;
-        case 64: MMU_FREC_DIM(4, 16); break;
-        default: MMU_FREC_DIM(4, 32); break;
+    const bool vec_dim = dim == 2 || dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64 || dim == 128;
+    const bool staged = vec_dim && (num_rep == 8 || num_rep == 4) && option(OPT_FORCE_STAGED) != 0;
+    if (!staged) {
+        // loop form (any num_rep; option force_staged = 0) and the generic-dimension kernel: one pass, no windows
+        const unsigned blocks = persistent_blocks(256, 8);
+#define MMU_FORCES(V, L)                                                                                          \
+    edge_forces_kernel<V, L><<<blocks, 256, 0, st>>>(rec, kept_hdr, neg, batch_kept, n_batches, num_rep,          \
+                                                     (uint32_t)rep_count, head, tail, grad_head, grad_tail, dim,  \
+                                                     a, b, seed, os, loss)
+        switch (dim) {
+            case 2: MMU_FORCES(2, 1); break;
+            case 4: MMU_FORCES(4, 1); break;
+            case 8: MMU_FORCES(4, 2); break;
+            case 16: MMU_FORCES(4, 4); break;
+            case 32: MMU_FORCES(4, 8); break;
+            case 64: MMU_FORCES(4, 16); break;
+            case 128: MMU_FORCES(4, 32); break;
+            default:
+                edge_forces_generic_kernel<<<blocks, 256, 0, st>>>(rec, kept_hdr, neg, batch_kept, n_batches, num_rep,
+                                                                   (uint32_t)rep_count, head, tail, grad_head, grad_tail,
+                                                                   dim, a, b, seed, os, loss);
+        }
+#undef MMU_FORCES
+        note_kernel(SITE_EDGE_FORCES, vec_dim ? "edge_forces_kernel<dim=%d>(num_rep=%d)" : "edge_forces_generic_kernel(dim=%d,num_rep=%d)",
+                    dim, num_rep);
+        MMU_LAUNCH_CHECK();
+        return MMU_OK;
     }
-#undef MMU_FREC_DIM
-#undef MMU_FREC
-    MMU_LAUNCH_CHECK();
+    // staged run form: 3 blocks per SM (__launch_bounds__(256, 3)), a grid of whole waves
+    const unsigned blocks = persistent_blocks(256, 3);
+    const bool windows = window_rows > 0 && window_rows < rep_count;
+    const int n_windows = windows ? (int)((rep_count + window_rows - 1) / window_rows) : 1;
+#define MMU_STAGED(V, L, RR, FASTV, WINV)                                                                        \
+    edge_forces_staged_kernel<V, L, RR, FASTV, WINV><<<blocks, 256, 0, st>>>(                                     \
+        rec, kept_hdr, neg, batch_kept, n_batches, (uint32_t)rep_count, head, tail, grad_head, grad_tail, a, b,  \
+        seed, os, loss, win_lo, win_len)
+#define MMU_STAGED_R(V, L, RR)                                         \
+    do {                                                               \
+        if (fast_math && windows) MMU_STAGED(V, L, RR, true, true);    \
+        else if (fast_math) MMU_STAGED(V, L, RR, true, false);         \
+        else if (windows) MMU_STAGED(V, L, RR, false, true);           \
+        else MMU_STAGED(V, L, RR, false, false);                       \
+    } while (0)
+#define MMU_STAGED_DIM(V, L)                          \
+    do {                                              \
+        if (num_rep == 8) MMU_STAGED_R(V, L, 8);      \
+        else MMU_STAGED_R(V, L, 4);                   \
+    } while (0)
+    for (int wdx = 0; wdx < n_windows; ++wdx) {
+        const uint32_t win_lo = windows ? (uint32_t)(wdx * window_rows) : 0u;
+        const uint32_t win_len = windows ? (uint32_t)(rep_count - win_lo < window_rows ? rep_count - win_lo : window_rows)
+                                         : (uint32_t)rep_count;
+        switch (dim) {
+            case 2: MMU_STAGED_DIM(2, 1); break;
+            case 4: MMU_STAGED_DIM(4, 1); break;
+            case 8: MMU_STAGED_DIM(4, 2); break;
+            case 16: MMU_STAGED_DIM(4, 4); break;
+            case 32: MMU_STAGED_DIM(4, 8); break;
+            case 64: MMU_STAGED_DIM(4, 16); break;
+            default: MMU_STAGED_DIM(4, 32); break;
+        }
+    }
+#undef MMU_STAGED_DIM
+#undef MMU_STAGED_R
+#undef MMU_STAGED
+    note_kernel(SITE_EDGE_FORCES, "edge_forces_staged_kernel<dim=%d,R=%d,%s,%s>%s", dim, num_rep, fast_math ? "fast" : "ieee",
+                windows ? "windowed" : "one-pass", windows ? " x tail windows" : "");
+    MMU_LAUNCH_CHECK_N(n_windows);
     return MMU_OK;
 }
 
-extern "C" int mmu_invert_forces(const int32_t *row, const int32_t *col, const int32_t *kept_pos,
-                                 const int32_t *kept_count, const int32_t *neg, const int32_t *batch_kept, int n_batches,
-                                 int batch_size, int num_rep, int64_t rep_count, const float *head, const float *data,
-                                 const float *sigma, const float *rho, float *grad_head, int dim, float a, float b,
-                                 uint64_t seed, const uint32_t *state, float *loss, mmu_stream_t stream) {
+extern "C" int mmu_invert_forces(const int32_t *kept_rec, const int32_t *kept_hdr, const int32_t *neg,
+                                 const int32_t *batch_kept, int n_batches, int num_rep, int64_t rep_count,
+                                 const float *head, const float *data, const float *sigma, const float *rho,
+                                 float *grad_head, int dim, float a, float b, uint64_t seed, const uint32_t *state,
+                                 float *loss, mmu_stream_t stream) {
     using namespace mmu;
-    MMU_CHECK_ARG(row && col && kept_pos && kept_count && batch_kept && head && data && sigma && rho && grad_head && state,
+    MMU_CHECK_ARG(kept_rec && kept_hdr && batch_kept && head && data && sigma && rho && grad_head && state,
                   "mmu_invert_forces: null pointer");
     MMU_CHECK_ARG(dim >= 1, "mmu_invert_forces: bad dim");
     MMU_CHECK_ARG(num_rep >= 0 && num_rep < INV_MAXP, "mmu_invert_forces: num_rep=%d outside [0,%d)", num_rep, INV_MAXP);
     MMU_CHECK_ARG(rep_count >= 1 && rep_count < ((int64_t)1 << 31), "mmu_invert_forces: bad rep_count");
-    MMU_CHECK_ARG(batch_size >= 1 && n_batches >= 1, "mmu_invert_forces: bad batch geometry");
-    invert_forces_kernel<<<persistent_blocks(256, 8), 256, 0, as_stream(stream)>>>(
-        row, col, kept_pos, kept_count, neg, batch_kept, n_batches, batch_size, num_rep, (uint32_t)rep_count, head, data,
-        sigma, rho, grad_head, dim, a, b, seed, reinterpret_cast<const OptState *>(state), loss);
+    MMU_CHECK_ARG(n_batches >= 1, "mmu_invert_forces: bad batch geometry");
+    MMU_CHECK_ARG((dim & 3) != 0 || ((reinterpret_cast<uintptr_t>(head) | reinterpret_cast<uintptr_t>(data) |
+                                      reinterpret_cast<uintptr_t>(grad_head)) & 15) == 0,
+                  "mmu_invert_forces: tables must be 16-byte aligned when dim is a multiple of 4");
+    const int4 *rec = reinterpret_cast<const int4 *>(kept_rec);
+    const OptState *os = reinterpret_cast<const OptState *>(state);
+    const unsigned blocks = persistent_blocks(256, 8);
+    if (num_rep == 8)
+        invert_forces_kernel<9><<<blocks, 256, 0, as_stream(stream)>>>(rec, kept_hdr, neg, batch_kept, n_batches, num_rep,
+                                                                       (uint32_t)rep_count, head, data, sigma, rho,
+                                                                       grad_head, dim, a, b, seed, os, loss);
+    else
+        invert_forces_kernel<0><<<blocks, 256, 0, as_stream(stream)>>>(rec, kept_hdr, neg, batch_kept, n_batches, num_rep,
+                                                                       (uint32_t)rep_count, head, data, sigma, rho,
+                                                                       grad_head, dim, a, b, seed, os, loss);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

@@ -57,36 +57,63 @@ def _coo(g: G.Graph) -> torch.Tensor:
     return _register(t, g)
 
 
+DEFAULT_KNN_DIST = "rows"      # multi-GPU kNN: query row-blocks per rank against the device-resident database
+
+
 class _Uploads:
     """Device copies of a list of inputs.  Host tensors are copied on a side stream in list order, so the
     upload of modality i+1 overlaps the graph construction of modality i (pinned host memory makes the
-    copies asynchronous); indexing waits for that tensor's copy only."""
+    copies asynchronous); indexing waits for that tensor's copy only.
 
-    def __init__(self, inputs):
+    Multi-GPU (one process per GPU): a rank uploads only ITS row block of a host tensor (1/W of the bytes over its
+    host link, the reference's single x.to(device) of model.py:634 split W ways) and the full matrix is assembled
+    on every GPU by one all-gather, device to device over NVLink -- instead of W ranks each pulling the whole input
+    through the host links."""
+
+    def __init__(self, inputs, shard: bool = False):
         native.require_cuda()                      # no CPU fallback: fail before touching any stream
         self._items = []
+        self.h2d_bytes = 0
         side = None
+        w, r = D.world(), D.rank()
         for x in inputs:
             if x.is_cuda:
-                self._items.append((x, None))
+                self._items.append((x, None, None))
                 continue
             if side is None:
                 side = torch.cuda.Stream()
             with torch.cuda.stream(side):
-                t = x.to(device, non_blocking=True)
+                if shard and w > 1 and x.dim() == 2 and x.shape[0] >= w:
+                    n = x.shape[0]
+                    lo, hi = D.row_block(n, r, w)
+                    per = D.block_size(n, w)
+                    blk = torch.zeros((per, x.shape[1]), dtype=x.dtype, device=device)
+                    if hi > lo:
+                        blk[: hi - lo].copy_(x[lo:hi], non_blocking=True)
+                    self.h2d_bytes += (hi - lo) * x.shape[1] * x.element_size()
+                    t, gather = blk, n
+                else:
+                    t, gather = x.to(device, non_blocking=True), None
+                    self.h2d_bytes += x.numel() * x.element_size()
                 ev = torch.cuda.Event()
                 ev.record(side)
-            self._items.append((t, ev))
+            self._items.append((t, ev, gather))
 
     def __len__(self):
         return len(self._items)
 
     def __getitem__(self, i):
-        t, ev = self._items[i]
+        t, ev, gather = self._items[i]
         if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
-            t.record_stream(torch.cuda.current_stream())
-            self._items[i] = (t, None)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            t.record_stream(cur)
+            if gather is not None:
+                import torch.distributed as dist
+                full = torch.empty((D.world() * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(full, t)          # every rank indexes the inputs in the same order
+                t = full[:gather]
+            self._items[i] = (t, None, None)
         return t
 
 
@@ -119,11 +146,19 @@ class UMAPEncoder:
         self.sigma_solver = os.environ.get("MMUMAP_SIGMA", "bisect")
         self.knn_method = None
 
-    def get_sigmas(self, dists: torch.Tensor, min_dists: torch.Tensor | None = None, num_iters: int | None = None) -> torch.Tensor:
-        """ref: model.py:33-61.  min_dists is accepted for signature parity; rho is the row minimum."""
+    def get_sigmas(self, dists: torch.Tensor, min_dists: torch.Tensor, num_iters: int = 20) -> torch.Tensor:
+        """ref: model.py:33-61.  sigma_i with sum_j exp(-(d_ij - rho_i)/sigma_i) = log2(k).  `min_dists` is rho
+        repeated along the row, as the reference passes it (model.py:199-200); the kernel takes rho as the row
+        minimum itself, so anything else is rejected rather than silently ignored.  `num_iters` is the Newton
+        iteration count (solver "newton"); the bisection solver always runs its 64 halvings."""
         dists = dists.to("cuda", torch.float32).reshape(-1, self.k_neighbors).contiguous()
+        if min_dists is not None:
+            md = torch.as_tensor(min_dists, dtype=torch.float32, device=dists.device).reshape(dists.shape[0], -1)
+            if not torch.equal(md.amin(dim=1), dists.amin(dim=1)) or not torch.equal(md.amin(dim=1), md.amax(dim=1)):
+                raise ValueError("get_sigmas: min_dists must be the row minimum of dists (rho), as in model.py:199")
         idx = torch.arange(self.k_neighbors, dtype=torch.int32, device=dists.device).repeat(dists.shape[0], 1)
-        _, _, sigma, _ = G.smooth_knn(idx, dists, self.sigma_solver, num_iters)
+        n_iter = int(num_iters) if self.sigma_solver == "newton" else max(64, int(num_iters))
+        _, _, sigma, _ = G.smooth_knn(idx, dists, self.sigma_solver, n_iter)
         return sigma
 
     def fuzzy_knn_graph(self, inputs: torch.Tensor, mode: str = "fit", query: torch.Tensor | None = None,
@@ -204,6 +239,7 @@ class UMAPMixture:
     def _engine_defaults(self):
         self.sample_stream = os.environ.get("MMUMAP_SAMPLE_STREAM", "device")
         self.last_optimizer = None
+        self.last_h2d_bytes = 0
 
     # ------------------------------------------------------------------ optimiser
     def _train(self, embeds, graphs, epochs: int, num_rep: int, lr: float, alpha: float, batch_size: int,
@@ -238,10 +274,11 @@ class UMAPMixture:
             batch_size: int = 512) -> None:
         """ref: model.py:483-508.  (The reference uploads the inputs twice, :496 and :634; here the device
         copies made for the graph stage are the ones kept as self.data.)"""
-        inputs = _Uploads(inputs)
+        inputs = _Uploads(inputs, shard=True)
         graphs, embeds = self.init(inputs, mode="fit")
         self.graphs = graphs
         self.data = [inputs[i] for i in range(len(inputs))]
+        self.last_h2d_bytes = inputs.h2d_bytes              # what THIS rank pulled over its host link
         self.embeds = self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="fit",
                                   desc=f"Training {self.num_encoders} encoders")
 

@@ -52,6 +52,23 @@ def batch_range(n_batches: int, r: int, w: int) -> tuple[int, int]:
     return (n_batches * r) // w, (n_batches * (r + 1)) // w
 
 
+def balanced_batch_range(cum_weight: list, r: int, w: int) -> tuple[int, int]:
+    """Row-batches owned by rank r when the shards are balanced by WEIGHT instead of by count: cum_weight[b] is
+    the sum of the edge weights of batches 0..b (the expected number of kept edges, model.py:432).  Rank r gets
+    the batches whose cumulative weight ends in (total*r/w, total*(r+1)/w]: contiguous, disjoint, covering, and
+    identical on every rank (a pure function of the replicated graph)."""
+    import bisect
+    nb = len(cum_weight)
+    total = cum_weight[-1] if nb else 0.0
+    if total <= 0.0:
+        return batch_range(nb, r, w)
+    cuts = [0] * (w + 1)
+    cuts[w] = nb
+    for i in range(1, w):
+        cuts[i] = min(nb, max(cuts[i - 1], bisect.bisect_left(cum_weight, total * i / w) + 1))
+    return cuts[r], cuts[r + 1]
+
+
 def item_range(n: int, r: int, w: int) -> tuple[int, int]:
     return (n * r) // w, (n * (r + 1)) // w
 

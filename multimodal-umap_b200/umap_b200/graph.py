@@ -37,15 +37,12 @@ class Graph:
 
     def to_sparse_coo(self) -> torch.Tensor:
         idx = torch.stack([self.row.long(), self.col.long()], dim=0)
-        t = torch.sparse_coo_tensor(idx, self.val, (self.n_rows, self.n_cols), is_coalesced=True)
-        t._mmu_graph = self
-        return t
+        # nothing of the engine is attached to the tensor: torch.save pickles a tensor's __dict__, and a checkpoint
+        # must stay loadable by the reference / with weights_only=True (impl/model.py keeps a weakref registry instead)
+        return torch.sparse_coo_tensor(idx, self.val, (self.n_rows, self.n_cols), is_coalesced=True)
 
     @staticmethod
     def from_sparse_coo(t: torch.Tensor) -> "Graph":
-        g = getattr(t, "_mmu_graph", None)
-        if g is not None:
-            return g
         native.require_cuda()
         t = t.coalesce() if not t.is_coalesced() else t
         dev = torch.device("cuda")
@@ -56,12 +53,7 @@ class Graph:
         counts = torch.bincount(idx[0], minlength=t.shape[0])
         rowptr = torch.zeros(t.shape[0] + 1, dtype=torch.int64, device=dev)
         rowptr[1:] = torch.cumsum(counts, 0)
-        g = Graph(t.shape[0], t.shape[1], rowptr, row, col, val)
-        try:
-            t._mmu_graph = g
-        except Exception:  # pragma: no cover
-            pass
-        return g
+        return Graph(t.shape[0], t.shape[1], rowptr, row, col, val)
 
     @staticmethod
     def from_fixed_degree(col: torch.Tensor, val: torch.Tensor, n_cols: int) -> "Graph":
@@ -123,7 +115,7 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         # multi-GPU fit: query row-blocks per rank, all-gather of the per-row results
         lo, hi = D.row_block(db.shape[0], D.rank(), D.world())
         with profiler.stage("knn", flops=2.0 * (hi - lo) * db.shape[0] * db.shape[1], kernel=kernel):
-            if os.environ.get("MMUMAP_KNN_DIST", "rows") == "ring":
+            if os.environ.get("MMUMAP_KNN_DIST", "rows") == "ring":      # default "rows": impl/model.py DEFAULT_KNN_DIST
                 # row-sharded DATABASE: each rank only touches its own rows of `db`; the shards rotate round
                 # the ranks peer-to-peer (NCCL send/recv over NVLink) under a running per-row top-k merge
                 return knn_ring(_f32c(db)[lo:hi].contiguous(), db.shape[0], k, exclude_self, search)

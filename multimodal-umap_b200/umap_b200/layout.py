@@ -35,7 +35,8 @@ def default_stream() -> str:
 class _Modality:
     """Device state of one table being optimised."""
 
-    def __init__(self, embed: torch.Tensor, graph: Graph, batch_size: int, ref: torch.Tensor | None, flat, offset: int):
+    def __init__(self, embed: torch.Tensor, graph: Graph, batch_size: int, ref: torch.Tensor | None, flat, offset: int,
+                 index: int, seed: int, host_stream: bool):
         dev = torch.device("cuda")
         n, d = embed.shape
         # p/g/m/v of all modalities live in four flat buffers: one all-reduce and one Adam launch per epoch
@@ -48,29 +49,61 @@ class _Modality:
         self.batch_size = batch_size
         self.n_batches = (self.count + batch_size - 1) // batch_size
         self.rep_count = self.ref.shape[0] if self.ref is not None else self.count
-        self.kept_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        # every modality draws from its own Philox key (the reference draws an independent rand / randint per
+        # modality, model.py:432,444): same key + same counters would give edge position p the same uniforms and
+        # the same negatives in every modality
+        self.seed = (int(seed) + index * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         self.batch_kept = torch.zeros(self.n_batches, dtype=torch.int32, device=dev)
-        # multi-GPU: this rank owns a range of row-batches, i.e. a contiguous range of edges
+        # multi-GPU: this rank owns a range of row-batches, i.e. a contiguous range of edges, chosen so that the
+        # ranks' expected kept-edge counts (sum of weights, model.py:432) are equal
         w, r = D.world(), D.rank()
-        self.b_lo, self.b_hi = D.batch_range(self.n_batches, r, w)
         if w == 1:
+            self.b_lo, self.b_hi = 0, self.n_batches
             self.e_lo, self.e_hi = 0, graph.nnz
         else:
+            ends = torch.arange(1, self.n_batches + 1, device=graph.rowptr.device, dtype=torch.int64) * batch_size
+            edge_end = graph.rowptr[ends.clamp(max=self.count)]
+            csum = torch.cumsum(graph.val.double(), 0)
+            cum_w = torch.where(edge_end > 0, csum[(edge_end - 1).clamp(min=0)], torch.zeros_like(edge_end, dtype=torch.float64))
+            self.b_lo, self.b_hi = D.balanced_batch_range(cum_w.cpu().tolist(), r, w)
             lo_row = min(self.b_lo * batch_size, self.count)
             hi_row = min(self.b_hi * batch_size, self.count)
             self.e_lo, self.e_hi = (int(v) for v in graph.rowptr[[lo_row, hi_row]].tolist())
-        self.kept_pos = torch.empty(max(self.e_hi - self.e_lo, 1), dtype=torch.int32, device=dev)
-        self.expected_kept = None            # sum of this rank's weights = E[kept edges per epoch] (model.py:432)
-        self.kept_rec = None                 # [n_edges, 4] int32 kept-edge records (device stream, record kernels)
+        n_edges = self.e_hi - self.e_lo
+        # E[kept edges per epoch] = this rank's sum of weights (Bernoulli(w), model.py:432); the record list holds
+        # that plus 10 standard deviations (variance <= sum w (1 - w) <= sum w), never more than the edge count
+        self.expected_kept = float(graph.val[self.e_lo:self.e_hi].double().sum().item()) if n_edges else 0.0
+        cap = n_edges if host_stream else min(n_edges, int(self.expected_kept + 10.0 * self.expected_kept ** 0.5) + 4096)
+        self.capacity = max(cap, 1)
+        self.kept_rec = torch.empty((self.capacity, 4), dtype=torch.int32, device=dev)
+        self.kept_hdr = self._new_hdr()
+        self.kept_pos = None                 # host stream: uploaded positions of the replayed draws
+        self.window_rows = None              # tail-window size of the force kernel, decided at the first launch
         # host copies for the replayed stream
         self._w_cpu = None
         self._rowptr_cpu = None
+
+    def _new_hdr(self):
+        return torch.tensor([0, self.capacity, 0, 0], dtype=torch.int32, device="cuda")
 
     def host_arrays(self):
         if self._w_cpu is None:
             self._w_cpu = self.graph.val.cpu()
             self._rowptr_cpu = self.graph.rowptr.cpu()
         return self._w_cpu, self._rowptr_cpu
+
+    def load_host_draws(self, kept: torch.Tensor, counts: torch.Tensor):
+        """Host sample stream: upload the replayed kept positions / per-batch counts and build the records."""
+        dev = self.p.device
+        n = int(kept.numel())
+        if self.kept_pos is None or self.kept_pos.numel() < max(n, 1):
+            self.kept_pos = torch.empty(max(n, 1, self.capacity), dtype=torch.int32, device=dev)
+        self.kept_pos[:n].copy_(kept.to(torch.int32).pin_memory(), non_blocking=True)
+        self.batch_kept.copy_(counts.to(torch.int32).pin_memory(), non_blocking=True)
+        g = self.graph
+        check(lib().mmu_edge_records(ptr(g.row), ptr(g.col), ptr(self.kept_pos), n, self.batch_size, ptr(self.kept_rec),
+                                     ptr(self.kept_hdr), stream()), "mmu_edge_records")
+        return n
 
 
 def replay_host_draws(mod: _Modality, num_rep: int):
@@ -135,24 +168,20 @@ class LayoutOptimizer:
         self.flat = tuple(torch.zeros(max(total, 1), dtype=torch.float32, device=dev) for _ in range(4))   # p, g, m, v
         self.total = total
         self.peer = self._peer_setup(total, dev)      # multi-GPU: parameters and gradients in NVLink peer memory
-        self.mods, off = [], 0
-        for i, (e, g) in enumerate(zip(embeds, graphs)):
-            self.mods.append(_Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
-                                       None if refs is None else refs[i], self.flat, off))
-            off += sizes[i]
         self.state = torch.zeros(native.OPT_STATE_WORDS, dtype=torch.int32, device=dev)
         check(lib().mmu_opt_state_init(ptr(self.state), stream()), "mmu_opt_state_init")
         if seed is None:
             # consume one draw from the global generator so torch.manual_seed controls the device stream too
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if self.sample_stream == "device" else 0
         self.seed = D.same_on_all_ranks(int(seed))
+        self.mods, off = [], 0
+        for i, (e, g) in enumerate(zip(embeds, graphs)):
+            self.mods.append(_Modality(e, g if isinstance(g, Graph) else Graph.from_sparse_coo(g), batch_size,
+                                       None if refs is None else refs[i], self.flat, off, i, self.seed,
+                                       self.sample_stream == "host"))
+            off += sizes[i]
         # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
         self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
-        # record-form kernels: measured equal to the position form on B200 (the force kernel is bound by
-        # L2 random-access throughput, not by the kept_pos -> row/col chain), so they stay opt-in
-        self.use_records = (self.sample_stream == "device" and mode in ("fit", "transform")
-                            and os.environ.get("MMUMAP_RECORDS", "0") == "1"
-                            and all(lib().mmu_edge_forces_records_supported(m.dim, self.num_rep) for m in self.mods))
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
         self.losses: list[float] = []
         self.done = 0                  # epochs completed (== the device-side epoch counter)
@@ -209,44 +238,51 @@ class LayoutOptimizer:
         return pr
 
     # ------------------------------------------------------------------ one epoch
-    def _forces(self, mod: _Modality, kept_pos, kept_count, neg, batch_kept):
+    def _window_rows(self, mod: _Modality) -> int:
+        """Rows per tail window of mmu_edge_forces (0 = one pass).  Tables that do not fit the L2 (p and, in fit
+        mode, g of the tail side: 10M x 2-D is 80 MB each) are processed in windows of ~48 MB so that the random
+        gathers / reds of a pass stay L2 resident; option sgd_window_mb: -1 automatic, 0 never, >0 window bytes."""
+        opt = native.get_option("sgd_window_mb")
+        if opt == 0 or self.mode == "invert":
+            return 0
+        row_bytes = mod.dim * 4 * (1 if self.mode == "transform" else 2)
+        table = mod.rep_count * row_bytes
+        if opt < 0 and table <= (100 << 20):
+            return 0
+        window = (48 << 20) if opt < 0 else (opt << 20)
+        n_win = max(1, -(-table // window))
+        if n_win == 1:
+            return 0
+        rows = -(-mod.rep_count // n_win)
+        return -(-rows // 1024) * 1024
+
+    def _forces(self, mod: _Modality, kept_rec, kept_hdr, neg, batch_kept):
         if self.mode == "invert":                                        # model.py:437,447
-            g, mi = mod.graph, self.mods.index(mod)
-            check(lib().mmu_invert_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg), ptr(batch_kept),
-                                          mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count, ptr(mod.p),
-                                          ptr(mod.ref), ptr(self.sigmas[mi]), ptr(self.rhos[mi]), ptr(mod.g), mod.dim,
-                                          self.a, self.b, self.seed, ptr(self.state), ptr(self.loss), stream()),
-                  "mmu_invert_forces")
+            mi = self.mods.index(mod)
+            check(lib().mmu_invert_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches,
+                                          self.num_rep, mod.rep_count, ptr(mod.p), ptr(mod.ref), ptr(self.sigmas[mi]),
+                                          ptr(self.rhos[mi]), ptr(mod.g), mod.dim, self.a, self.b, mod.seed,
+                                          ptr(self.state), ptr(self.loss), stream()), "mmu_invert_forces")
             return
         tail = mod.ref if self.mode == "transform" else mod.p
         grad_tail = None if self.mode == "transform" else mod.g
-        g = mod.graph
         if profiler.enabled():
-            if mod.expected_kept is None:
-                mod.expected_kept = float(g.val[mod.e_lo:mod.e_hi].sum().item())
             # SURVEY.md 8(d): per kept edge (2+R) row reads of d*4 B and as many row accumulations in fit mode
             # (one, the query row, in transform mode), + 12 B of edge indices
             rows_touched = (2 + self.num_rep) * 2 if grad_tail is not None else (2 + self.num_rep) + 1
             nbytes = mod.expected_kept * (rows_touched * mod.dim * 4 + 12)
             with profiler.stage("edge_forces", bytes=nbytes, edge_updates=mod.expected_kept * (1 + self.num_rep)):
-                self._launch_forces(mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail)
+                self._launch_forces(mod, kept_rec, kept_hdr, neg, batch_kept, tail, grad_tail)
             return
-        self._launch_forces(mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail)
+        self._launch_forces(mod, kept_rec, kept_hdr, neg, batch_kept, tail, grad_tail)
 
-    def _launch_forces(self, mod, kept_pos, kept_count, neg, batch_kept, tail, grad_tail):
-        g = mod.graph
-        if kept_pos is None:                                             # record form (device stream)
-            check(lib().mmu_edge_forces_records(ptr(mod.kept_rec), ptr(kept_count), ptr(batch_kept), mod.n_batches,
-                                                self.num_rep, mod.rep_count, ptr(mod.p), ptr(tail), ptr(mod.g),
-                                                ptr(grad_tail), mod.dim, self.a, self.b, self.seed, ptr(self.state),
-                                                ptr(self.loss), int(self.fast_math), stream()),
-                  "mmu_edge_forces_records")
-            return
-        check(lib().mmu_edge_forces(ptr(g.row), ptr(g.col), ptr(kept_pos), ptr(kept_count), ptr(neg),
-                                    ptr(batch_kept), mod.n_batches, mod.batch_size, self.num_rep, mod.rep_count,
-                                    ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a, self.b,
-                                    self.seed, ptr(self.state), ptr(self.loss), int(self.fast_math), stream()),
-              "mmu_edge_forces")
+    def _launch_forces(self, mod, kept_rec, kept_hdr, neg, batch_kept, tail, grad_tail):
+        if mod.window_rows is None:
+            mod.window_rows = self._window_rows(mod)
+        check(lib().mmu_edge_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches, self.num_rep,
+                                    mod.rep_count, ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a,
+                                    self.b, mod.seed, ptr(self.state), ptr(self.loss), int(self.fast_math),
+                                    mod.window_rows, stream()), "mmu_edge_forces")
 
     def _infonce(self, src: _Modality, dst: _Modality, perm, neg, stream_id: int):
         num = min(src.count, dst.count)
@@ -262,30 +298,17 @@ class LayoutOptimizer:
             if host:
                 kept, neg, counts = replay_host_draws(mod, self.num_rep)
                 self.edge_updates += int(kept.numel()) * (1 + self.num_rep)
-                n = kept.numel()
-                mod.kept_pos[:n].copy_(kept.pin_memory(), non_blocking=True)
-                mod.kept_count.copy_(torch.tensor([n], dtype=torch.int32).pin_memory(), non_blocking=True)
-                mod.batch_kept.copy_(counts.pin_memory(), non_blocking=True)
+                n = mod.load_host_draws(kept, counts)
                 neg_d = neg.pin_memory().to(dev, non_blocking=True) if n else torch.zeros(1, dtype=torch.int32, device=dev)
-                self._forces(mod, mod.kept_pos, mod.kept_count, neg_d, mod.batch_kept)
-            elif self.use_records:
-                g = mod.graph
-                if mod.kept_rec is None:
-                    mod.kept_rec = torch.empty((max(mod.e_hi - mod.e_lo, 1), 4), dtype=torch.int32, device=dev)
-                with profiler.stage("edge_sample", level=2):
-                    check(lib().mmu_edge_sample_records(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi,
-                                                        mod.batch_size, mod.n_batches, self.seed, ptr(self.state),
-                                                        ptr(mod.kept_rec), ptr(mod.kept_count), ptr(mod.batch_kept),
-                                                        stream()), "mmu_edge_sample_records")
-                self._forces(mod, None, mod.kept_count, None, mod.batch_kept)
+                self._forces(mod, mod.kept_rec, mod.kept_hdr, neg_d, mod.batch_kept)
             else:
                 g = mod.graph
                 with profiler.stage("edge_sample", level=2):
-                    check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
-                                                      mod.n_batches, self.seed, ptr(self.state), ptr(mod.kept_pos),
-                                                      ptr(mod.kept_count), ptr(mod.batch_kept), stream()),
-                          "mmu_edge_sample_range")
-                self._forces(mod, mod.kept_pos, mod.kept_count, None, mod.batch_kept)
+                    check(lib().mmu_edge_sample_range(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi,
+                                                      mod.batch_size, mod.n_batches, mod.seed, ptr(self.state),
+                                                      ptr(mod.kept_rec), ptr(mod.kept_hdr), ptr(mod.batch_kept),
+                                                      stream()), "mmu_edge_sample_range")
+                self._forces(mod, mod.kept_rec, mod.kept_hdr, None, mod.batch_kept)
         self._epoch_tail()
 
     def _epoch_tail(self):
@@ -357,8 +380,9 @@ class LayoutOptimizer:
         dev = torch.device("cuda")
         bufs = []
         for mod in self.mods:
-            bufs.append([(mod.kept_pos, mod.kept_count, mod.batch_kept),
-                         (torch.empty_like(mod.kept_pos), torch.zeros_like(mod.kept_count), torch.zeros_like(mod.batch_kept))])
+            bufs.append([(mod.kept_rec, mod.kept_hdr, mod.batch_kept),
+                         (torch.empty_like(mod.kept_rec), mod._new_hdr(), torch.zeros_like(mod.batch_kept))])
+            mod.all_hdrs = [b[1] for b in bufs[-1]]
         sampled = [None, None]
         consumed = [None, None]
         base = self.done
@@ -376,9 +400,9 @@ class LayoutOptimizer:
                 for mi, mod in enumerate(self.mods):
                     g = mod.graph
                     kp, kc, bk = bufs[mi][b]
-                    check(lib().mmu_edge_sample_at(ptr(g.row), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size, mod.n_batches,
-                                                   self.seed, base + e, ptr(self.state), ptr(kp), ptr(kc), ptr(bk),
-                                                   side.cuda_stream), "mmu_edge_sample_at")
+                    check(lib().mmu_edge_sample_at(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
+                                                   mod.n_batches, mod.seed, base + e, ptr(self.state), ptr(kp), ptr(kc),
+                                                   ptr(bk), side.cuda_stream), "mmu_edge_sample_at")
                 ev = torch.cuda.Event()
                 ev.record(side)
                 sampled[b] = ev
@@ -399,7 +423,7 @@ class LayoutOptimizer:
             main.wait_event(sampled[b])
             for mi, mod in enumerate(self.mods):
                 kp, kc, bk = bufs[mi][b]
-                mod.kept_count = kc                      # kept_last_epoch() reads the buffer in use
+                mod.kept_hdr = kc                        # kept_last_epoch() reads the buffer in use
                 self._forces(mod, kp, kc, None, bk)
             ev = torch.cuda.Event()
             ev.record(main)
@@ -425,7 +449,7 @@ class LayoutOptimizer:
                      and (mode == "1" or (mode == "auto" and small))
                      and (D.world() == 1 or (self.peer is None and os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1")))
         if not use_graph:
-            overlap = (self.sample_stream == "device" and not self.use_records and self.mode in ("fit", "transform")
+            overlap = (self.sample_stream == "device" and self.mode in ("fit", "transform")
                        and epochs > 1 and os.environ.get("MMUMAP_OVERLAP_SAMPLE", "1") == "1")
             if overlap:
                 self._run_overlapped(epochs)
@@ -458,10 +482,15 @@ class LayoutOptimizer:
         return self.result()
 
     def result(self):
-        return [m.p.clone() for m in self.mods]
+        out = [m.p.clone() for m in self.mods]
+        # one read of the overflow flags per run (the clone above already orders after the last epoch)
+        flags = torch.stack([h[2] for m in self.mods for h in getattr(m, "all_hdrs", [m.kept_hdr])])
+        if bool(flags.any().item()):
+            raise native.NativeError("kept-edge list overflow: an epoch kept more edges than sum(w) + 10 sigma")
+        return out
 
     def kept_last_epoch(self) -> int:
         """Kept edges of the last epoch over all ranks."""
-        t = torch.stack([m.kept_count[0] for m in self.mods]).sum().to(torch.int64).reshape(1)
+        t = torch.stack([m.kept_hdr[0] for m in self.mods]).sum().to(torch.int64).reshape(1)
         D.all_reduce_sum(t)
         return int(t.item())

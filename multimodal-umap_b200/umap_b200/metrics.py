@@ -28,6 +28,32 @@ def retrieval_accuracy(src_embed: torch.Tensor, dst_embed: torch.Tensor, k: int)
     return float(correct.item()) / (2 * n)
 
 
+def retrieval_accuracies(src_embed: torch.Tensor, dst_embed: torch.Tensor, ks) -> dict:
+    """retrieval_accuracy for several k from ONE search at max(ks): the engine's rows are sorted by
+    (distance, index), so the k nearest are the first k columns."""
+    n = src_embed.shape[0]
+    a = src_embed.detach().to("cuda", torch.float32).contiguous()
+    b = dst_embed.detach().to("cuda", torch.float32).contiguous()
+    own = torch.arange(n, device=a.device, dtype=torch.int32)[:, None]
+    kmax = max(ks)
+    fwd, _ = G.knn_graph(a, b, kmax, exclude_self=False)
+    bwd, _ = G.knn_graph(b, a, kmax, exclude_self=False)
+    return {k: float(((fwd[:, :k] == own).any(dim=1).sum() + (bwd[:, :k] == own).any(dim=1).sum()).item()) / (2 * n)
+            for k in ks}
+
+
+def knn_test_multi(model, embed_fn, data: dict, cfg, ks=(1, 5)) -> dict:
+    """knn_test of validation.py:40-84 for several k with one transform per modality pair."""
+    mats = [data[key] for key in data]
+    accs = {k: [] for k in ks}
+    for src in range(len(mats)):
+        for dst in range(src + 1, len(mats)):
+            e = embed_fn(model, [mats[src], mats[dst]], [src, dst], cfg)
+            for k, v in retrieval_accuracies(e[0], e[1], ks).items():
+                accs[k].append(v)
+    return {k: float(torch.tensor(v).mean().item()) for k, v in accs.items()}
+
+
 def knn_test(model, embed_fn, data: dict, cfg, k: int = 5) -> float:
     """knn_test of validation.py:40-84 with the batched retrieval."""
     mats = [data[key] for key in data]

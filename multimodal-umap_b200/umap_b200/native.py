@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libmmumap_b200.so")
 MAX_K = 64
 KNN_TC_MAX_K = 32
 OPT_STATE_WORDS = 8
+KEPT_HDR_WORDS = 4          # [count, capacity, overflow flag, reserved]
 PEER_MAX = 16
 SIGMA_BISECT = 0
 SIGMA_NEWTON = 1
@@ -33,6 +34,9 @@ _SIGNATURES = {
     "mmu_launch_count": (c_uint64, []),
     "mmu_launch_count_add": (None, [c_uint64]),
     "mmu_device_info": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_set_option": (c_int, [ctypes.c_char_p, c_int64]),
+    "mmu_get_option": (c_int, [ctypes.c_char_p, c_void_p]),
+    "mmu_last_kernel": (ctypes.c_char_p, [ctypes.c_char_p]),
     "mmu_knn_exact_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,
                                   c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
@@ -55,23 +59,17 @@ _SIGNATURES = {
                                    c_double, c_void_p, c_void_p]),
     "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
     "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
-    "mmu_edge_sample": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p]),
-    "mmu_edge_sample_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p]),
-    "mmu_edge_sample_at": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_int64, c_void_p, c_void_p,
-                                   c_void_p, c_void_p, c_void_p]),
-    "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
-                                c_void_p, c_void_p, c_int, c_void_p]),
-    "mmu_edge_sample_records": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mmu_edge_forces_records_supported": (c_int, [c_int, c_int]),
-    "mmu_edge_forces_records": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
-                                        c_void_p, c_int, c_float, c_float, c_uint64, c_void_p, c_void_p, c_int, c_void_p]),
-    "mmu_invert_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64,
-                                  c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_sample_range": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_sample_at": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_records": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_edge_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_float, c_float, c_uint64, c_void_p, c_void_p, c_int,
+                                c_int64, c_void_p]),
+    "mmu_invert_forces": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_uint64, c_void_p, c_void_p,
+                                  c_void_p]),
     "mmu_infonce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                             c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),
     "mmu_infonce_range": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
@@ -79,6 +77,7 @@ _SIGNATURES = {
     "mmu_infonce_bidir": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p,
                                   c_void_p]),
+    "mmu_roof_random_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_uint64, c_int, c_int, c_void_p, c_void_p]),
     "mmu_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_void_p,
                               c_int, c_void_p]),
 }
@@ -131,6 +130,22 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_option(name: str, value: int) -> None:
+    """A/B switch of the kernels (include/mmumap.h: mmu_set_option); the environment is read once at load."""
+    check(lib().mmu_set_option(name.encode(), int(value)), f"mmu_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = c_int64()
+    check(lib().mmu_get_option(name.encode(), ctypes.byref(v)), f"mmu_get_option({name})")
+    return int(v.value)
+
+
+def last_kernel(site: str) -> str:
+    """Kernel variant the launch site chose last ("edge_forces", "knn_candidates", ...)."""
+    return (lib().mmu_last_kernel(site.encode()) or b"").decode()
 
 
 def device_info():

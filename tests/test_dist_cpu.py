@@ -99,6 +99,19 @@ def test_partition_arithmetic():
         for w in (1, 2, 8):
             rs = [D.batch_range(nb, r, w) for r in range(w)]
             assert rs[0][0] == 0 and rs[-1][1] == nb and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+    # shards balanced by weight: contiguous, covering, and each rank's weight within one batch of total / w
+    rng = np.random.default_rng(4)
+    for nb in (1, 7, 621):
+        wts = rng.random(nb) ** 3 * 100.0                       # strongly non-uniform batches
+        cum = np.cumsum(wts).tolist()
+        for w in (1, 2, 4, 8):
+            rs = [D.balanced_batch_range(cum, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == nb and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            assert all(lo <= hi for lo, hi in rs)
+            if nb >= 8 * w:
+                share = [wts[lo:hi].sum() for lo, hi in rs]
+                assert max(share) <= wts.sum() / w + wts.max() + 1e-9
+    assert D.balanced_batch_range([0.0, 0.0, 0.0], 1, 2) == D.batch_range(3, 1, 2)
 
 
 @pytest.mark.timeout(300)

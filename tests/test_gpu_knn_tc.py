@@ -156,7 +156,7 @@ def test_deep_candidate_pool_certifies_what_one_list_cannot():
 
 
 @pytest.mark.parametrize("n,d,kind", [(12000, 768, "bert"), (5000, 4096, "vae")])
-def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind, monkeypatch):
+def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind):
     """The candidate kernel has two forms (knn_tc.cu: cta_group::2 CTA pairs for long rows, one CTA per
     query block otherwise) and the pair form walks a large database in windows, carrying the per-row
     lists from launch to launch.  All of them must give the exhaustive kernel's result bit for bit;
@@ -174,13 +174,19 @@ def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind, monkeypatch):
     q = x[: 128 * 37 + 5].contiguous()                       # 38 query blocks in query mode, 37 full
     qi, qd = G.knn_exact_simt(q, x, 15, False)
     qi, qd = qi.cpu().numpy(), qd.cpu().numpy()
-    for env in ({"MMUMAP_KNN_WINDOW_MB": "1"}, {"MMUMAP_KNN_WINDOW_MB": "0"}, {"MMUMAP_KNN_CTA_PAIRS": "0"}):
-        for key, val in env.items():
-            monkeypatch.setenv(key, val)
-        ti, td, st = _tc(x, x, 15, True)
-        _same(ti, td, si, sd)
-        assert st["fallback_rows"] <= 0.02 * n, (env, st)
-        ti, td, st = _tc(q, x, 15, False)
-        _same(ti, td, qi, qd)
-        for key in env:
-            monkeypatch.delenv(key)
+    from umap_b200 import native
+    defaults = {"knn_window_mb": native.get_option("knn_window_mb"), "knn_cta_pairs": native.get_option("knn_cta_pairs")}
+    try:
+        for opts in ({"knn_window_mb": 1}, {"knn_window_mb": 0}, {"knn_cta_pairs": 0}):
+            for key, val in opts.items():
+                native.set_option(key, val)
+            ti, td, st = _tc(x, x, 15, True)
+            _same(ti, td, si, sd)
+            assert st["fallback_rows"] <= 0.02 * n, (opts, st)
+            ti, td, st = _tc(q, x, 15, False)
+            _same(ti, td, qi, qd)
+            for key in opts:
+                native.set_option(key, defaults[key])
+    finally:
+        for key, val in defaults.items():
+            native.set_option(key, val)
