@@ -444,9 +444,12 @@ def run_b200(args, workload, data):
         torch.manual_seed(1234)
         return util_mod.train(resident, cfg)
 
+    h2d_rank = [0]
+
     def fit_e2e():
         torch.manual_seed(1234)
         model = util_mod.train(host, cfg)                   # H2D copies happen inside (model.py:496,634)
+        h2d_rank[0] = int(model.last_h2d_bytes)             # what this rank pulled over its host link
         return [e.detach().cpu() for e in model.embeds]     # D2H read of the result
 
     # Spin-up, then the W warm-up steps: a fresh box needs a few seconds of load before clocks and power state
@@ -563,9 +566,12 @@ def run_b200(args, workload, data):
         roofs = measure_roofs(dev, [(nm, n, d_out) for (nm, n, _, _) in workload["mods"]])
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    hb = torch.tensor([h2d_rank[0]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)
     total_ms, e2e_s = float(t[0]), float(t[1])
+    h2d_total = int(hb[0])
     if rank != 0:
         return None
     ms_per_step = total_ms / args.steps
@@ -633,8 +639,8 @@ def run_b200(args, workload, data):
                    "spinup_s": 0.0 if args.quick else SPINUP_S,
                    "parallelism": f"kNN query-row blocks x{world}, optimiser edge shards x{world}" if world > 1 else "1 GPU"},
         "e2e": {"value": None if e2e_s != e2e_s else e2e_s, "unit": "s",
-                "h2d_bytes_per_step": int(model.last_h2d_bytes) * world,
-                "h2d_bytes_per_rank": int(model.last_h2d_bytes),
+                "h2d_bytes_per_step": h2d_total,
+                "h2d_bytes_per_rank": h2d_rank[0],
                 "d2h_bytes_per_step": int(sum(r * d * 4 for r in rows))},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -317,6 +317,20 @@ int mmu_adam_step_peer(const uint64_t *peer_params, const uint64_t *peer_grads, 
                        int world, int rank, double beta1, double beta2, double eps, const uint32_t *state,
                        mmu_stream_t stream);
 
+/* The whole multi-GPU epoch tail in ONE launch (the default exchange; the two calls above remain as its A/B partner):
+ * flag barrier "gradients complete" -> reduce this rank's 1/W shard of the W partial gradients + Adam + store the new
+ * parameters to all W replicas + store zeros over that shard of all W gradient buffers (the gradient clear) -> flag
+ * barrier "shard delivered" -> advance the optimiser state words (what mmu_opt_state_advance does; the bias
+ * corrections of this step are formed from the old state inside the kernel).  mc_params / mc_grads: NVSwitch multicast
+ * addresses of the same symmetric buffers (0 = not available): with them the reduction is one
+ * multimem.ld_reduce.add and each broadcast one multimem.st per 16 bytes instead of W peer accesses.
+ * done_counter: one zero-initialised uint32 in LOCAL device memory (grid-completion counter, left at zero).
+ * seq must increase by one per call; flag slots as for mmu_peer_barrier. */
+int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *peer_grads, const uint64_t *peer_flags,
+                        uint64_t mc_params, uint64_t mc_grads, float *m, float *v, int64_t n, int world, int rank,
+                        uint32_t seq, double lr, double beta1, double beta2, double eps, uint32_t *state,
+                        uint32_t *done_counter, mmu_stream_t stream);
+
 /* ----------------------------------------------------------------------------------
  * Measured roof of the random-access kernels (reported by bench.py beside the HBM copy peak; not on the fit path).
  * Touches n_rows_touched uniformly random rows of a [n_rows x row_floats] table the way mmu_edge_forces does: one

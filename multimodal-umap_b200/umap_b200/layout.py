@@ -26,6 +26,7 @@ BETA1, BETA2, EPS = 0.9, 0.999, 1e-8          # torch.optim.Adam defaults (model
 INFONCE_NEG = 9                               # n_neg + 1 draws per anchor (model.py:364,383)
 INFONCE_CHUNK = 1000                          # model.py:369
 INFONCE_TAU = 0.5                             # model.py:364
+AUTO_WINDOW_MB = 48                           # p + g bytes of the tail rows of one force-kernel window (see _window_rows)
 
 
 def default_stream() -> str:
@@ -227,9 +228,22 @@ class LayoutOptimizer:
             dist.barrier()                                             # every rank's flags are zero before the first use
             bases = [int(b) for b in hdl.buffer_ptrs]
             arr = ctypes.c_uint64 * w
+            # NVSwitch multicast mapping of the same buffer (0 when the system has none): multimem.ld_reduce / multimem.st
+            mc = 0
+            if os.environ.get("MMUMAP_PEER_MULTIMEM", "1") == "1":
+                try:
+                    mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                except Exception:                                      # noqa: BLE001
+                    mc = 0
+            mc_ok = torch.tensor([1 if mc else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(mc_ok, op=dist.ReduceOp.MIN)               # all ranks take the same kernel form
+            if int(mc_ok.item()) == 0:
+                mc = 0
             pr = {"sym": sym, "hdl": hdl, "seq": 0, "cap": cap,
                   "params": arr(*bases), "grads": arr(*[b + 4 * cap for b in bases]),
-                  "flags": arr(*[b + 8 * cap for b in bases])}
+                  "flags": arr(*[b + 8 * cap for b in bases]),
+                  "mc_params": mc, "mc_grads": (mc + 4 * cap) if mc else 0,
+                  "done": torch.zeros(1, dtype=torch.int32, device=dev)}
             _PEER_CACHE["buf"] = pr
         sym, cap = pr["sym"], pr["cap"]
         # the previous user's last epoch ended with the slot-1 barrier: no peer still reads these buffers
@@ -247,9 +261,12 @@ class LayoutOptimizer:
             return 0
         row_bytes = mod.dim * 4 * (1 if self.mode == "transform" else 2)
         table = mod.rep_count * row_bytes
-        if opt < 0 and table <= (100 << 20):
+        # automatic: only where a row is smaller than a 32-byte DRAM sector (d <= 4: every random access would move
+        # 2-4x its payload) AND the tables overflow the L2.  Measured on one B200: 10M x 2-D 22.0 -> 15.3 ms/epoch
+        # with 48 MB windows; 1M x 16-D (64-byte rows, no sector waste) 1.5 -> 3.1 ms/epoch, i.e. a loss.
+        if opt < 0 and (table <= (100 << 20) or mod.dim * 4 > 16):
             return 0
-        window = (48 << 20) if opt < 0 else (opt << 20)
+        window = (AUTO_WINDOW_MB << 20) if opt < 0 else (opt << 20)
         n_win = max(1, -(-table // window))
         if n_win == 1:
             return 0
@@ -350,6 +367,18 @@ class LayoutOptimizer:
             # -> [all parameters delivered] -> clear my gradient buffer
             pr, w, r = self.peer, D.world(), D.rank()
             pr["seq"] += 1
+            if os.environ.get("MMUMAP_PEER_TAIL", "fused") == "fused":
+                # ONE launch: barrier + shard reduce + Adam + replica store + gradient clear + barrier + state advance
+                with profiler.stage("epoch_tail", level=2):
+                    check(lib().mmu_epoch_tail_peer(pr["params"], pr["grads"], pr["flags"], pr["mc_params"], pr["mc_grads"],
+                                                    ptr(m), ptr(v), self.total, w, r, pr["seq"], self.lr, BETA1, BETA2, EPS,
+                                                    ptr(self.state), ptr(pr["done"]), stream()), "mmu_epoch_tail_peer")
+                self.done += 1
+                if self.loss is not None:
+                    D.all_reduce_sum(self.loss)
+                    self.losses.append(float(self.loss.item()))
+                    self.loss.zero_()
+                return
             check(lib().mmu_opt_state_advance(ptr(self.state), self.lr, BETA1, BETA2, stream()), "mmu_opt_state_advance")
             with profiler.stage("adam", level=2):
                 check(lib().mmu_peer_barrier(pr["flags"], w, r, 0, pr["seq"], stream()), "mmu_peer_barrier")
