@@ -172,6 +172,43 @@ int mmu_spmm_csr(const int64_t *rowptr, const int32_t *col, const float *val, in
  * (torch.linalg.eigh's convention).  The dense Rayleigh-Ritz / orthonormalisation steps of the spectral
  * initialisation without a host round trip.  ref: model.py:232 (inside torch.lobpcg) */
 int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_stream_t stream);
+/* the same, returning at once when *skip_flag != 0 (device int; the control block of the block eigensolver below) */
+int mmu_eigh_small_flag(const float *a, int n, float *lam, float *v, const int *skip_flag, mmu_stream_t stream);
+
+/* Block eigensolver operations: the dense n x B block algebra (B in {8,16,32}) of the spectral initialisation's
+ * Chebyshev-filtered subspace iteration, with every scalar of the iteration in a device-resident control block so
+ * that the host enqueues whole outer iterations without a synchronisation.        ref: model.py:221-234 (embed_all /
+ * torch.lobpcg's Rayleigh-Ritz and orthonormalisation steps).
+ * Control block: mmu_block_ctl_words() floats; word 0 (int) = converged flag, word 1 (int) = Rayleigh-Ritz steps
+ * taken, word 2 = largest residual of the wanted pairs, word 3 = filter edge.  Every call below returns at once when
+ * the flag is set.
+ *   mmu_block_spmm    y = alpha A x + beta x + gamma z with (alpha, beta, gamma) from the control block:
+ *                     coef_slot 0 = (1,0,0), 1 = first Chebyshev step (1/e, -c/e, 0), 2 = later steps (2/e, -2c/e, -1);
+ *                     z may alias y.
+ *   mmu_block_gram    g = x^T y (B x B, row-major), deterministic two-stage reduction (workspace of
+ *                     mmu_block_gram_workspace_bytes(b)); mode 0 as is, 1 symmetrised, 2 symmetrised and scaled to unit
+ *                     diagonal with dinv[i] = 1/sqrt(g_ii) returned.
+ *   mmu_block_rotate  x_out = x_in T (T = tmat, columns reversed if flip); with ax_in also ax_out = ax_in T and the
+ *                     control block's column residuals += |ax_out_j - lam'_j x_out_j|^2.  In place allowed.
+ *   mmu_block_ritz    after mmu_eigh_small(x^T A x): Ritz values, residual, converged flag (residual < tol or
+ *                     max_iters reached), next filter edge and Chebyshev coefficients.
+ *   mmu_block_svqb    tmat = D^-1 V Lambda^-1/2 from the eigen-decomposition (lam, v) of the Gram matrix (dinv from
+ *                     mode 2, or NULL): x tmat has orthonormal columns. */
+int mmu_block_ctl_words(void);
+int mmu_block_ctl_init(float *ctl, mmu_stream_t stream);
+int mmu_block_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n, const float *x, int b,
+                   const float *ctl, int coef_slot, const float *z, float *y, mmu_stream_t stream);
+size_t mmu_block_gram_workspace_bytes(int b);
+int mmu_block_gram(const float *x, const float *y, int64_t n, int b, int mode, void *workspace, float *g, float *dinv,
+                   const float *ctl, mmu_stream_t stream);
+int mmu_block_rotate(const float *x_in, float *x_out, const float *ax_in, float *ax_out, int64_t n, int b,
+                     const float *tmat, int flip, const float *lam, float *ctl, mmu_stream_t stream);
+int mmu_block_ritz(const float *lam, int b, int m, float tol, int max_iters, float *ctl, mmu_stream_t stream);
+int mmu_block_svqb(const float *lam, const float *v, const float *dinv, int b, float *tmat, const float *ctl,
+                   mmu_stream_t stream);
+/* Cholesky-QR step: tmat = L^-T with g = L L^T (g a B x B Gram matrix close to the identity, as after an SVQB pass):
+ * x tmat has orthonormal columns.  One small CTA, a few microseconds. */
+int mmu_block_cholqr(const float *g, int b, float *tmat, const float *ctl, mmu_stream_t stream);
 
 /* y = alpha * (A x) + beta * x + gamma * z  (z nullable; z may alias y): one three-term
  * Chebyshev recurrence step of the spectral initialisation per launch.  ref: model.py:221-234 */

@@ -18,7 +18,9 @@ constexpr int EIGH_MAX_SWEEPS = 16;
 constexpr int EIGH_THREADS = 512;
 
 __global__ void __launch_bounds__(EIGH_THREADS)
-eigh_small_kernel(const float *__restrict__ a_in, int n, float *__restrict__ lam_out, float *__restrict__ v_out) {
+eigh_small_kernel(const float *__restrict__ a_in, int n, float *__restrict__ lam_out, float *__restrict__ v_out,
+                  const int *__restrict__ skip_flag) {
+    if (skip_flag && *skip_flag) return;         // the enclosing iteration has converged (block_eig.cu control block)
     extern __shared__ float sm[];
     const int ne = (n + 1) & ~1;                 // even number of players; index n (if any) is a dummy
     const int np = ne / 2;                       // rotations per step
@@ -130,7 +132,7 @@ eigh_small_kernel(const float *__restrict__ a_in, int n, float *__restrict__ lam
 
 }  // namespace mmu
 
-extern "C" int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_stream_t stream) {
+extern "C" int mmu_eigh_small_flag(const float *a, int n, float *lam, float *v, const int *skip_flag, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(a && lam && v, "mmu_eigh_small: null pointer");
     MMU_CHECK_ARG(n >= 1 && n <= EIGH_MAX_N, "mmu_eigh_small: n=%d outside [1,%d]", n, EIGH_MAX_N);
@@ -139,7 +141,11 @@ extern "C" int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_s
     if (first_use_on_device(SITE_EIGH_SMALL))     // the attribute is per device
         MMU_CUDA(cudaFuncSetAttribute(eigh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(float) * (4 * EIGH_MAX_N * EIGH_MAX_N + 4 * EIGH_MAX_N))));
-    eigh_small_kernel<<<1, EIGH_THREADS, smem, as_stream(stream)>>>(a, n, lam, v);
+    eigh_small_kernel<<<1, EIGH_THREADS, smem, as_stream(stream)>>>(a, n, lam, v, skip_flag);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
+}
+
+extern "C" int mmu_eigh_small(const float *a, int n, float *lam, float *v, mmu_stream_t stream) {
+    return mmu_eigh_small_flag(a, n, lam, v, nullptr, stream);
 }

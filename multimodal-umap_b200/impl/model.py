@@ -264,7 +264,8 @@ class UMAPMixture:
                     for i in range(n_modes)]
         opt = LayoutOptimizer(embeds, [_as_graph(g) for g in graphs], self.a, self.b, num_rep, lr, alpha,
                               batch_size, mode=mode, refs=refs, sigmas=sigmas, rhos=rhos,
-                              sample_stream=getattr(self, "sample_stream", None))
+                              sample_stream=getattr(self, "sample_stream", None),
+                              seed=getattr(self, "_shard_seed", None), norm_batches=getattr(self, "_shard_norm_batches", None))
         with profiler.stage("optimise", epochs=epochs):
             out = opt.run(epochs)
         self.last_optimizer = opt
@@ -291,9 +292,53 @@ class UMAPMixture:
     def transform(self, inputs: list, epochs: int, data_indices: list | None = None, num_rep: int = 8,
                   lr: float = 0.2, alpha: float = 0.5, batch_size: int = 512):
         """ref: model.py:527-555."""
+        sharded = self._sharded_rows(inputs, batch_size)
+        if sharded is not None:
+            return self._run_sharded(sharded, "transform", inputs, epochs, data_indices, num_rep, lr, alpha, batch_size)
         graphs, embeds = self.init(inputs, mode="transform", data_indices=data_indices)
         return self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode="transform",
                            data_indices=data_indices, desc=f"Embedding {len(embeds)} modalities")
+
+    # ------------------------------------------------------------------ multi-GPU: independent query rows
+    def _sharded_rows(self, inputs, batch_size: int):
+        """Multi-GPU transform / inverse_transform (device sample stream): the queries are independent -- only the
+        query's own row receives gradient (model.py:399-401,416) -- so rank r takes a block of whole row-batches of
+        every input and runs the single-GPU path on it with NO exchange; the blocks are all-gathered at the end.
+        Returns the per-input (lo, hi, per) blocks, or None when the call should not be sharded."""
+        w = D.world()
+        if w == 1 or getattr(self, "sample_stream", "device") != "device" or os.environ.get("MMUMAP_SHARD_TRANSFORM", "1") != "1":
+            return None
+        align = batch_size * 128 // math.gcd(batch_size, 128)          # whole row-batches AND whole 128-row kNN tiles
+        blocks = []
+        for x in inputs:
+            n = x.shape[0] if x.dim() > 1 else 1
+            if n < 2 * w * align:
+                return None
+            lo, hi = D.row_block(n, D.rank(), w, align)
+            blocks.append((lo, hi, D.block_size(n, w, align), n))
+        return blocks
+
+    def _run_sharded(self, blocks, mode, inputs, epochs, data_indices, num_rep, lr, alpha, batch_size):
+        r = D.rank()
+        local = [x[lo:hi] for x, (lo, hi, _, _) in zip(inputs, blocks)]
+        outs = [None] * len(inputs)
+        base = int(torch.randint(0, 2 ** 62, (1,)).item())               # same draw on every rank (same generator state)
+        if all(hi > lo for (lo, hi, _, _) in blocks):
+            self._shard_seed = (base + r * 0x632BE59BD9B4E019) & 0x3FFFFFFFFFFFFFFF
+            self._shard_norm_batches = [-(-n // batch_size) for (_, _, _, n) in blocks]
+            try:
+                with D.local_only():
+                    graphs, embeds = self.init(local, mode=mode, data_indices=data_indices)
+                    outs = self._train(embeds, graphs, epochs, num_rep, lr, alpha, batch_size, mode=mode,
+                                       data_indices=data_indices, desc=f"{mode} of {len(embeds)} modalities (row block {r})")
+            finally:
+                self._shard_seed = self._shard_norm_batches = None
+        full = []
+        for o, (lo, hi, per, n), x in zip(outs, blocks, inputs):
+            width = o.shape[1] if o is not None else (self.out_dim if mode == "transform" else self.data[0].shape[1])
+            loc = o.detach() if o is not None else torch.zeros((0, width), dtype=torch.float32, device="cuda")
+            full.append(D.all_gather_rows(loc, n, per).requires_grad_(True))
+        return full
 
     def inverse_transform(self, inputs: list, epochs: int, data_indices: list | None = None, num_rep: int = 8,
                           lr: float = 0.2, alpha: float = 0.5, batch_size: int = 512):

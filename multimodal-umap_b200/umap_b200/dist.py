@@ -26,12 +26,54 @@ import torch
 import torch.distributed as dist
 
 
+_LOCAL_ONLY = 0
+
+
 def world() -> int:
+    if _LOCAL_ONLY:
+        return 1
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 def rank() -> int:
+    if _LOCAL_ONLY:
+        return 0
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+class local_only:
+    """Inside this context the partitioning helpers see ONE rank: the enclosed work is this rank's own shard of an
+    embarrassingly parallel stage (the transform of independent query rows) and runs the single-GPU path, with no
+    exchange.  real_world() / real_rank() still report the process group."""
+
+    def __enter__(self):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _LOCAL_ONLY
+        _LOCAL_ONLY -= 1
+        return False
+
+
+def real_world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def real_rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, per: int) -> torch.Tensor:
+    """Concatenate the ranks' row blocks (rank r holds rows [r*per, r*per + local.shape[0])) into the full
+    [n_total, ...] tensor on every rank."""
+    w = real_world()
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    full = torch.empty((w * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, pad)
+    return full[:n_total].contiguous()
 
 
 def row_block(n: int, r: int, w: int, align: int = 128) -> tuple[int, int]:

@@ -26,7 +26,7 @@ BETA1, BETA2, EPS = 0.9, 0.999, 1e-8          # torch.optim.Adam defaults (model
 INFONCE_NEG = 9                               # n_neg + 1 draws per anchor (model.py:364,383)
 INFONCE_CHUNK = 1000                          # model.py:369
 INFONCE_TAU = 0.5                             # model.py:364
-AUTO_WINDOW_MB = 48                           # p + g bytes of the tail rows of one force-kernel window (see _window_rows)
+AUTO_WINDOW_MB = 80                           # p + g bytes of the tail rows of one force-kernel window (see _window_rows)
 
 
 def default_stream() -> str:
@@ -148,7 +148,7 @@ _PEER_CACHE: dict = {}
 class LayoutOptimizer:
     def __init__(self, embeds, graphs, a: float, b: float, num_rep: int, lr: float, alpha: float,
                  batch_size: int, mode: str = "fit", refs=None, sample_stream: str | None = None,
-                 seed: int | None = None, track_loss: bool = False, sigmas=None, rhos=None):
+                 seed: int | None = None, track_loss: bool = False, sigmas=None, rhos=None, norm_batches=None):
         native.require_cuda()
         if mode not in ("fit", "transform", "invert"):
             raise ValueError(f"Invalid mode: {mode}")
@@ -181,6 +181,9 @@ class LayoutOptimizer:
                                        None if refs is None else refs[i], self.flat, off, i, self.seed,
                                        self.sample_stream == "host"))
             off += sizes[i]
+            # 1/n_batches of the loss (model.py:453).  A rank that optimises its own block of query rows on its own
+            # (sharded transform) still normalises by the batch count of the WHOLE query set.
+            self.mods[-1].n_batches_norm = int(norm_batches[i]) if norm_batches is not None else self.mods[-1].n_batches
         # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
         self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
@@ -262,8 +265,10 @@ class LayoutOptimizer:
         row_bytes = mod.dim * 4 * (1 if self.mode == "transform" else 2)
         table = mod.rep_count * row_bytes
         # automatic: only where a row is smaller than a 32-byte DRAM sector (d <= 4: every random access would move
-        # 2-4x its payload) AND the tables overflow the L2.  Measured on one B200: 10M x 2-D 22.0 -> 15.3 ms/epoch
-        # with 48 MB windows; 1M x 16-D (64-byte rows, no sector waste) 1.5 -> 3.1 ms/epoch, i.e. a loss.
+        # 2-4x its payload) AND the tables overflow the L2.  Measured on one B200, 10M x 2-D (80 + 80 MB), ms/epoch:
+        # one pass 22.0, windows of 32 MB 18.1, 48 MB 15.3, 64 MB 12.7, 80 MB (two windows of 40 + 40 MB) 10.5 -- the
+        # largest slice that still stays L2 resident wins, every extra pass re-reads the records and re-draws the
+        # negatives; 1M x 16-D (64-byte rows, no sector waste): 1.5 -> 3.1 ms/epoch, i.e. a loss.
         if opt < 0 and (table <= (100 << 20) or mod.dim * 4 > 16):
             return 0
         window = (AUTO_WINDOW_MB << 20) if opt < 0 else (opt << 20)
@@ -276,7 +281,7 @@ class LayoutOptimizer:
     def _forces(self, mod: _Modality, kept_rec, kept_hdr, neg, batch_kept):
         if self.mode == "invert":                                        # model.py:437,447
             mi = self.mods.index(mod)
-            check(lib().mmu_invert_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches,
+            check(lib().mmu_invert_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches_norm,
                                           self.num_rep, mod.rep_count, ptr(mod.p), ptr(mod.ref), ptr(self.sigmas[mi]),
                                           ptr(self.rhos[mi]), ptr(mod.g), mod.dim, self.a, self.b, mod.seed,
                                           ptr(self.state), ptr(self.loss), stream()), "mmu_invert_forces")
@@ -296,7 +301,7 @@ class LayoutOptimizer:
     def _launch_forces(self, mod, kept_rec, kept_hdr, neg, batch_kept, tail, grad_tail):
         if mod.window_rows is None:
             mod.window_rows = self._window_rows(mod)
-        check(lib().mmu_edge_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches, self.num_rep,
+        check(lib().mmu_edge_forces(ptr(kept_rec), ptr(kept_hdr), ptr(neg), ptr(batch_kept), mod.n_batches_norm, self.num_rep,
                                     mod.rep_count, ptr(mod.p), ptr(tail), ptr(mod.g), ptr(grad_tail), mod.dim, self.a,
                                     self.b, mod.seed, ptr(self.state), ptr(self.loss), int(self.fast_math),
                                     mod.window_rows, stream()), "mmu_edge_forces")

@@ -54,6 +54,18 @@ _SIGNATURES = {
     "mmu_spmm_csr_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float, c_void_p,
                                    c_float, c_void_p, c_void_p]),
     "mmu_eigh_small": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_eigh_small_flag": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_block_ctl_words": (c_int, []),
+    "mmu_block_ctl_init": (c_int, [c_void_p, c_void_p]),
+    "mmu_block_spmm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p]),
+    "mmu_block_gram_workspace_bytes": (c_size_t, [c_int]),
+    "mmu_block_gram": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_block_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
+    "mmu_block_ritz": (c_int, [c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "mmu_block_svqb": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mmu_block_cholqr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_int, c_uint32, c_void_p]),
     "mmu_adam_step_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double, c_double,
                                    c_double, c_void_p, c_void_p]),

@@ -74,6 +74,99 @@ def _orthonormalise(x: torch.Tensor) -> torch.Tensor:
     return x @ (v * lam.rsqrt())
 
 
+BLOCK_WIDTHS = (8, 16, 32)          # block widths the device-resident block operations are instantiated for
+
+
+def block_width(out_dim: int) -> int:
+    """Columns of the iteration block: the out_dim + 1 wanted vectors plus guard vectors (the convergence rate of a
+    filtered subspace iteration is set by the gap to the first eigenvalue OUTSIDE the block)."""
+    m = out_dim + 1
+    return 8 if m <= 5 else 16 if m <= 12 else 32 if m <= 24 else -(-(m + 8) // 4) * 4
+
+
+def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 30, degree: int = 10) -> torch.Tensor:
+    """Chebyshev-filtered subspace iteration with EVERY step on the engine's own kernels (csrc/block_eig.cu) and every
+    scalar of the iteration (Ritz values, residual, convergence flag, filter edge, Chebyshev coefficients) in a
+    device-resident control block: the host enqueues whole outer iterations and reads the flag once per chunk of
+    iterations instead of once per iteration.  Same mathematics and output contract as `spectral_chebfsi` below.
+
+    One outer iteration = 1 SpMM (A x) + Gram (x^T A x) + 32x32 Jacobi + fused rotation of x and A x with the column
+    residuals + the Ritz bookkeeping kernel + `degree` fused three-term SpMM steps + two SVQB orthonormalisations
+    (Gram scaled to unit diagonal -> Jacobi -> T = D^-1 V Lambda^-1/2 -> rotation): ~27 launches of this library."""
+    import ctypes
+    n, dev = g.n_rows, g.val.device
+    m = out_dim + 1
+    b = block_width(out_dim)
+    L = lib()
+    st = stream()
+    aval = normalized_adjacency(g)
+    deg = torch.zeros(n, dtype=torch.float32, device=dev)
+    deg.index_add_(0, g.row.long(), g.val)
+    bufs = [torch.empty((n, b), dtype=torch.float32, device=dev) for _ in range(4)]
+    x, ax, y0, y1 = bufs
+    x.copy_(torch.randn((n, b), dtype=torch.float32, device=dev))
+    x[:, 0] = deg.clamp(min=1e-6).sqrt()                    # the known top eigenvector of A
+    ctl = torch.empty(L.mmu_block_ctl_words(), dtype=torch.float32, device=dev)
+    flag = ctl.view(torch.int32)
+    check(L.mmu_block_ctl_init(ptr(ctl), st), "mmu_block_ctl_init")
+    ws = torch.empty(L.mmu_block_gram_workspace_bytes(b), dtype=torch.uint8, device=dev)
+    gm = torch.empty((b, b), dtype=torch.float32, device=dev)
+    tm = torch.empty((b, b), dtype=torch.float32, device=dev)
+    vm = torch.empty((b, b), dtype=torch.float32, device=dev)
+    lam = torch.empty(b, dtype=torch.float32, device=dev)
+    dinv = torch.empty(b, dtype=torch.float32, device=dev)
+    rp, col = ptr(g.rowptr), ptr(g.col)
+
+    def orthonormalise(src, dst, scaled):
+        """scaled: dst = src (src^T src)^-1/2 (SVQB) with the Gram matrix first brought to unit diagonal, which is the
+        column equalisation the filtered block needs (p(theta_j) spans orders of magnitude).  Not scaled: the second,
+        polishing pass over an already nearly orthonormal block, done as Cholesky-QR."""
+        check(L.mmu_block_gram(ptr(src), ptr(src), n, b, 2 if scaled else 1, ptr(ws), ptr(gm), ptr(dinv), ptr(ctl), st), "gram")
+        if scaled:
+            check(L.mmu_eigh_small_flag(ptr(gm), b, ptr(lam), ptr(vm), ptr(flag), st), "eigh")
+            check(L.mmu_block_svqb(ptr(lam), ptr(vm), ptr(dinv), b, ptr(tm), ptr(ctl), st), "svqb")
+        else:
+            # the block is already nearly orthonormal (an SVQB pass ran just before): Cholesky-QR, a few microseconds
+            check(L.mmu_block_cholqr(ptr(gm), b, ptr(tm), ptr(ctl), st), "cholqr")
+        check(L.mmu_block_rotate(ptr(src), ptr(dst), None, None, n, b, ptr(tm), 0, None, ptr(ctl), st), "rotate")
+
+    orthonormalise(x, x, True)
+
+    def outer():
+        nonlocal x, ax, y0, y1
+        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(x), b, ptr(ctl), 0, None, ptr(ax), st), "spmm")
+        check(L.mmu_block_gram(ptr(x), ptr(ax), n, b, 1, ptr(ws), ptr(gm), None, ptr(ctl), st), "gram")
+        check(L.mmu_eigh_small_flag(ptr(gm), b, ptr(lam), ptr(vm), ptr(flag), st), "eigh")
+        # x <- x V, ax <- ax V (Ritz vectors, descending), column residuals |A x_j - theta_j x_j|^2 into the control block
+        check(L.mmu_block_rotate(ptr(x), ptr(x), ptr(ax), ptr(ax), n, b, ptr(vm), 1, ptr(lam), ptr(ctl), st), "rotate")
+        check(L.mmu_block_ritz(ptr(lam), b, m, tol, max_iter, ptr(ctl), st), "ritz")
+        # Chebyshev filter of degree `degree` on [-1, cut]: T_1 from x, T_2 with z = x, then z aliases the output
+        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(x), b, ptr(ctl), 1, None, ptr(y1), st), "cheb1")
+        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(y1), b, ptr(ctl), 2, ptr(x), ptr(y0), st), "cheb2")
+        cur, prev = y0, y1
+        for _ in range(3, degree + 1):
+            check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(cur), b, ptr(ctl), 2, ptr(prev), ptr(prev), st), "chebk")
+            cur, prev = prev, cur
+        # equalise the column lengths (unit-diagonal Gram) and orthonormalise twice; the result becomes the new block.
+        # After convergence every kernel above and below returns at once, so x keeps the converged Ritz vectors.
+        orthonormalise(cur, prev, True)
+        orthonormalise(prev, x, False)
+
+    chunk = 4
+    iters = 0
+    while True:
+        for _ in range(chunk):
+            outer()
+        done, iters = flag[:2].tolist()                      # ONE synchronisation per chunk of outer iterations
+        if done or iters >= max_iter:
+            break
+        chunk = 2
+    if os.environ.get("MMUMAP_SPECTRAL_DEBUG") == "1":
+        print(f"  chebfsi(device) n={n} b={b}: {iters} Rayleigh-Ritz steps, residual {float(ctl[2]):.3e}, cut {float(ctl[3]):.4f}")
+    vecs = x[:, 1:m]
+    return (vecs / vecs.norm(dim=0, keepdim=True)).contiguous()
+
+
 def spectral_chebfsi(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 30, degree: int = 10) -> torch.Tensor:
     """Chebyshev-filtered subspace iteration (Zhou-Saad) for the out_dim+1 largest eigenpairs of
     A = D^-1/2 S D^-1/2, i.e. the smallest of the reference's L = I - A + 1e-6 I (model.py:221-230),
@@ -146,5 +239,10 @@ def spectral_init(g: Graph, out_dim: int, method: str | None = None) -> torch.Te
     if method == "lobpcg":
         return spectral_lobpcg(g, out_dim)
     if method == "chebfsi":
+        # device-resident form for the instantiated block widths (out_dim <= 23); the torch-assisted form otherwise
+        if block_width(out_dim) in BLOCK_WIDTHS:
+            return spectral_chebfsi_device(g, out_dim)
+        return spectral_chebfsi(g, out_dim)
+    if method == "chebfsi_torch":
         return spectral_chebfsi(g, out_dim)
     raise ValueError(f"unknown spectral method {method!r}")

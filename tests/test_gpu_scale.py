@@ -115,6 +115,41 @@ def test_c4_shaped_slice_knn_bit_exact():
     _check_rows_vs_oracle(x_cpu.numpy(), ti, td, 30, 128, 13)
 
 
+def test_c2_spectral_init_residuals_at_full_size():
+    """embed_all's contract (model.py:211-234) at BASELINE.json configs[1] size, where a dense eigensolve is out of
+    reach: the 16 vectors returned for the 158,915-row text graph are unit norm, mutually orthogonal, orthogonal to the
+    trivial eigenvector D^1/2 1, and eigenvectors of L = I - D^-1/2 S D^-1/2 + 1e-6 I to torch.lobpcg's own tolerance
+    (residual |L v - lambda v| < 3.5e-4 ... 2e-3 with fp32 operator applications), with Rayleigh quotients in [0, 1)."""
+    from umap_b200 import graph as G
+    from umap_b200.spectral import normalized_adjacency, spectral_init
+    b = _bench()
+    x = b.make_data(b.WORKLOADS["c2"])["texts"].cuda()
+    idx, dist = G.knn_graph(x, x, 15, True)
+    col, w, _, _ = G.smooth_knn(idx, dist, "bisect")
+    g = G.fuzzy_union(col, w)
+    torch.manual_seed(0)
+    v = spectral_init(g, 16)
+    n = g.n_rows
+    assert tuple(v.shape) == (n, 16) and bool(torch.isfinite(v).all())
+    v64 = v.double()
+    assert torch.allclose(v64.norm(dim=0), torch.ones(16, dtype=torch.float64, device=v.device), atol=1e-4)
+    gram = v64.T @ v64
+    assert float((gram - torch.eye(16, dtype=torch.float64, device=v.device)).abs().max()) < 1e-3
+    aval = normalized_adjacency(g)
+    av = torch.zeros_like(v64)
+    av.index_add_(0, g.row.long(), aval.double()[:, None] * v64[g.col.long()])
+    lv = (1.0 + 1e-6) * v64 - av                                  # L v
+    lam = (v64 * lv).sum(0)
+    res = (lv - v64 * lam).norm(dim=0)
+    assert float(res.max()) < 2e-3, res
+    assert float(lam.min()) > -1e-4 and float(lam.max()) < 1.0, lam
+    deg = torch.zeros(n, dtype=torch.float64, device=v.device).index_add_(0, g.row.long(), g.val.double())
+    triv = deg.clamp(min=1e-6).sqrt()
+    triv /= triv.norm()
+    assert float((triv @ v64).abs().max()) < 1e-3
+    _record("c2_texts_spectral", {"max_residual": float(res.max()), "lambda_min": float(lam.min()), "lambda_max": float(lam.max())})
+
+
 # --------------------------------------------------------------------------- C1 as such
 C1_REF = {"reference_200": 0.871, "newton_200": (0.834, 0.847), "bisect_200": (0.775, 0.780),
           "newton_600": (0.956, 0.957), "bisect_600": (0.960, 0.962)}      # BASELINE.md section 2

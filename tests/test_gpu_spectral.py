@@ -24,7 +24,7 @@ def _graph(n, d, k, seed, centers):
     return G.fuzzy_union(col, w)
 
 
-@pytest.mark.parametrize("method", ["chebfsi", "lobpcg"])
+@pytest.mark.parametrize("method", ["chebfsi", "chebfsi_torch", "lobpcg"])
 @pytest.mark.parametrize("n,out_dim,centers", [(1500, 2, 3), (2500, 8, 5)])
 def test_spectral_init_solves_the_reference_operator(method, n, out_dim, centers):
     from umap_b200.spectral import spectral_init
