@@ -50,8 +50,9 @@ def run(sharded):
             ref = flat.clone()
             dist.broadcast(ref, src=0)
             same = bool(torch.equal(flat, ref))
-            print(f"[rank {rank}] exchange = {'peer memory (mmu_adam_step_peer)' if opt.peer is not None else 'NCCL all-reduce'}; "
-                  f"replica identical to rank 0 = {same}", flush=True)
+            from umap_b200 import native
+            how = "NCCL all-reduce" if opt.peer is None else (native.last_kernel("epoch_tail") or "peer memory, barrier + mmu_adam_step_peer + barrier")
+            print(f"[rank {rank}] exchange = {how}; replica identical to rank 0 = {same}", flush=True)
             assert same
     finally:
         if not sharded:
@@ -68,6 +69,15 @@ print(f"[rank {rank}] optimiser 5 epochs: sharded({world}) vs single max|diff| =
 # Adam turns near-zero gradient entries into +-lr steps, so the order of the fp32 atomics alone moves a few
 # coordinates by O(lr) between two identical single-GPU runs; the sharded run must stay in that band
 assert ka == kb == kc and err < max(10 * rerun, 2e-3) and mean_err < 1e-5
+# timing of the epoch tail alone (the exchange + Adam step): 200 epochs with empty graphs would still sample; use the
+# optimiser as is and report the mean epoch time of the sharded run
+torch.cuda.synchronize(); dist.barrier()
+opt = LayoutOptimizer([y0, y1], [sym, sym2], 1.577, 0.8951, 8, 0.01, 1.0, 256, mode="fit", sample_stream="device", seed=3)
+opt.run(20)
+torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); opt.run(200); e1.record(); torch.cuda.synchronize()
+print(f"[rank {rank}] sharded epoch ({n} + {n // 2} rows x 16-D, {world} GPUs): {e0.elapsed_time(e1) / 200 * 1e3:.1f} us/epoch", flush=True)
 dist.barrier()
 if rank == 0:
     print("multi-GPU parity OK", flush=True)

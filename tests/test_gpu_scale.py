@@ -117,8 +117,7 @@ def test_c4_shaped_slice_knn_bit_exact():
 
 def test_c2_spectral_init_residuals_at_full_size():
     """embed_all's contract (model.py:211-234) at BASELINE.json configs[1] size, where a dense eigensolve is out of
-    reach: the 16 vectors returned for the 158,915-row text graph are unit norm, mutually orthogonal, orthogonal to the
-    trivial eigenvector D^1/2 1, and eigenvectors of L = I - D^-1/2 S D^-1/2 + 1e-6 I to torch.lobpcg's own tolerance
+    reach: the 16 vectors returned for the 158,915-row text graph are unit norm, mutually orthogonal, and eigenvectors of L = I - D^-1/2 S D^-1/2 + 1e-6 I to torch.lobpcg's own tolerance
     (residual |L v - lambda v| < 3.5e-4 ... 2e-3 with fp32 operator applications), with Rayleigh quotients in [0, 1)."""
     from umap_b200 import graph as G
     from umap_b200.spectral import normalized_adjacency, spectral_init
@@ -143,10 +142,9 @@ def test_c2_spectral_init_residuals_at_full_size():
     res = (lv - v64 * lam).norm(dim=0)
     assert float(res.max()) < 2e-3, res
     assert float(lam.min()) > -1e-4 and float(lam.max()) < 1.0, lam
-    deg = torch.zeros(n, dtype=torch.float64, device=v.device).index_add_(0, g.row.long(), g.val.double())
-    triv = deg.clamp(min=1e-6).sqrt()
-    triv /= triv.norm()
-    assert float((triv @ v64).abs().max()) < 1e-3
+    # (No orthogonality check against the trivial eigenvector D^1/2 1: this graph has 64 well separated clusters,
+    # i.e. ~64 eigenvalues within 1e-3 of lambda_min, and embed_all drops "the first" of the computed vectors
+    # (model.py:234), which in a near-degenerate cluster is an arbitrary direction of it -- for torch.lobpcg too.)
     _record("c2_texts_spectral", {"max_residual": float(res.max()), "lambda_min": float(lam.min()), "lambda_max": float(lam.max())})
 
 
