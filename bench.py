@@ -522,6 +522,7 @@ def run_b200(args, workload, data):
         nq = 100000
         qd = make_data(workload, seed=7, n_rows=nq)
         qdev = [v.to(dev) for v in qd.values()]
+        util_mod.embed(model, qdev, list(range(len(qdev))), cfg)       # untimed first call (kernel loads, allocations)
         barrier()
         tr0, tr1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tr0.record()
@@ -596,7 +597,16 @@ def run_b200(args, workload, data):
     # the edge work and all of the Adam work divided by world on the peer path
     bytes_epoch = sum(12 * z for z in nnz) + kept * (2 + OPT["num_rep"]) * d * 4 * 2 + sum(28 * r * d for r in rows)
     edge_updates = kept * (1 + OPT["num_rep"])
-    forces = stages.get("edge_forces", {"ms": 0.0, "calls": 0, "bytes": 0.0, "edge_updates": 0.0})
+    # N > 1 replays whole epochs from CUDA graphs (no per-kernel events inside): the force kernel's launch time then
+    # comes from the instrumented pass that follows the timed region (same kernels, launched one by one)
+    forces_from = "timed region"
+    forces = stages.get("edge_forces")
+    forces_scale = 1.0
+    if not forces or not forces.get("calls"):
+        forces, forces_from = fine.get("edge_forces"), "instrumented pass after the timed region (the timed region replays CUDA graphs)"
+        forces_scale = float(steps)            # one instrumented fit against `steps` timed fits
+    if not forces or not forces.get("calls"):
+        forces = {"ms": 0.0, "calls": 0, "bytes": 0.0, "edge_updates": 0.0}
     forces_gbs = forces["bytes"] / (forces["ms"] * 1e-3) / 1e9 if forces["ms"] > 0 else 0.0
     kf = facts.get("knn_candidates", {})
     ff = facts.get("edge_forces", {})
@@ -621,11 +631,11 @@ def run_b200(args, workload, data):
                 "traffic": ff.get("dram_bytes_per_launch"),
                 "effective_bound": "l2 (p and g tables %.0f MB, resident in the 126 MB L2)" % table_mb if table_mb < 100 else "hbm",
                 "l2_roof": l2_roof, "peak_source": peak_src,
-                "share_of_step": forces["ms"] / total_ms if total_ms else None,
+                "share_of_step": forces["ms"] * forces_scale / total_ms if total_ms else None, "timed_in": forces_from,
                 "ms_per_launch": forces["ms"] / max(forces["calls"], 1),
                 "edge_updates_per_s": forces["edge_updates"] / (forces["ms"] * 1e-3) if forces["ms"] > 0 else None,
                 "ncu": ff or None}
-    dominant, other = (roof_sgd, roof_knn) if forces["ms"] >= knn["ms"] else (roof_knn, roof_sgd)
+    dominant, other = (roof_sgd, roof_knn) if forces["ms"] * forces_scale >= knn["ms"] else (roof_knn, roof_sgd)
     sgd_gbs_job = bytes_epoch * epochs / (opt_ms * 1e-3) / 1e9 if opt_ms else None
     line = {
         "metric": "umap_fit_seconds", "value": ms_per_step / 1e3, "unit": "s", "n_gpus": world,

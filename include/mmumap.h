@@ -248,7 +248,8 @@ int mmu_edge_sample_range(const int32_t *row, const int32_t *col, const float *w
 
 /* The same with the epoch number given by the host (epoch >= 0) instead of read from `state`:
  * lets the sampling of epoch e+1 run on a second stream while the forces of epoch e execute (it
- * does not depend on the embeddings).  epoch = -1 reads state->epoch. */
+ * does not depend on the embeddings).  epoch = -1 reads state->epoch; epoch = -2 reads state->epoch + 1 (the next
+ * epoch's sample inside a captured CUDA graph, which cannot carry a per-epoch argument). */
 int mmu_edge_sample_at(const int32_t *row, const int32_t *col, const float *w, int64_t edge_lo,
                        int64_t edge_hi, int batch_size, int n_batches, uint64_t seed, int64_t epoch,
                        const uint32_t *state, int32_t *kept_rec, int32_t *kept_hdr, int32_t *batch_kept,
@@ -361,8 +362,10 @@ int mmu_adam_step_peer(const uint64_t *peer_params, const uint64_t *peer_grads, 
  * corrections of this step are formed from the old state inside the kernel).  mc_params / mc_grads: NVSwitch multicast
  * addresses of the same symmetric buffers (0 = not available): with them the reduction is one
  * multimem.ld_reduce.add and each broadcast one multimem.st per 16 bytes instead of W peer accesses.
- * done_counter: one zero-initialised uint32 in LOCAL device memory (grid-completion counter, left at zero).
- * seq must increase by one per call; flag slots as for mmu_peer_barrier. */
+ * done_counter: TWO zero-initialised uint32 in LOCAL device memory: [0] grid-completion counter (left at zero), [1] the
+ * barrier sequence number kept on the device.  seq > 0: the host's sequence number (must increase by one per call);
+ * seq == 0: the kernel uses and advances done_counter[1] -- no per-epoch argument, so the epoch can be captured into a
+ * CUDA graph and replayed.  Flag slots as for mmu_peer_barrier. */
 int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *peer_grads, const uint64_t *peer_flags,
                         uint64_t mc_params, uint64_t mc_grads, float *m, float *v, int64_t n, int world, int rank,
                         uint32_t seq, double lr, double beta1, double beta2, double eps, uint32_t *state,

@@ -44,7 +44,9 @@ edge_sample_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ 
                    int64_t epoch_override) {
     // edges [edge_lo, nnz) of the global COO; the Philox counter is the GLOBAL quad index, so a
     // shard draws exactly what the single-GPU run draws for the same edges
-    const uint32_t epoch = epoch_override >= 0 ? (uint32_t)epoch_override : st->epoch;
+    // epoch_override >= 0: the host's epoch number; -1: the device-resident counter; -2: the counter + 1 (the NEXT epoch's
+    // sample, drawn while this epoch's forces run, inside a captured CUDA graph that has no per-epoch arguments)
+    const uint32_t epoch = epoch_override >= 0 ? (uint32_t)epoch_override : st->epoch + (epoch_override == -2 ? 1u : 0u);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n4 = (nnz + 3) >> 2;

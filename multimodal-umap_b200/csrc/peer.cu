@@ -131,10 +131,13 @@ template <bool MC, int WT>      // WT: compile-time world size (0 = run-time) so
 __global__ void __launch_bounds__(256)
 epoch_tail_peer_kernel(PeerPtrs params, PeerPtrs grads, PeerPtrs flags, const float4 *__restrict__ mc_params,
                        const float4 *__restrict__ mc_grads, float *__restrict__ m, float *__restrict__ v, int64_t lo4,
-                       int64_t hi4, int world_rt, int rank, uint32_t seq, double lr, double beta1d, double beta2d,
+                       int64_t hi4, int world_rt, int rank, uint32_t seq_arg, double lr, double beta1d, double beta2d,
                        float beta2, float omb1, float omb2, float eps, OptState *__restrict__ st,
-                       unsigned int *__restrict__ done_counter) {
+                       unsigned int *__restrict__ done_counter, uint32_t *__restrict__ seq_word) {
     const int world = WT ? WT : world_rt;
+    // barrier sequence number: given by the host, or (seq_arg == 0) kept in device memory and advanced by this kernel,
+    // so that the launch has no per-epoch argument and an epoch can be replayed from a CUDA graph
+    const uint32_t seq = seq_arg ? seq_arg : *seq_word + 1u;
     __shared__ float s_step[2];
     if (threadIdx.x == 0) {
         const uint32_t step = st->step + 1;                       // the step this launch applies
@@ -218,6 +221,7 @@ epoch_tail_peer_kernel(PeerPtrs params, PeerPtrs grads, PeerPtrs flags, const fl
             st->epoch = st->epoch + 1;
             st->step_size = s_step[0];
             st->bc2_sqrt = s_step[1];
+            if (!seq_arg) *seq_word = seq;
         }
     }
 }
@@ -274,6 +278,7 @@ extern "C" int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *
                                    uint64_t mc_params, uint64_t mc_grads, float *m, float *v, int64_t n, int world, int rank,
                                    uint32_t seq, double lr, double beta1, double beta2, double eps, uint32_t *state,
                                    uint32_t *done_counter, mmu_stream_t stream) {
+    // done_counter[0]: grid-completion counter; done_counter[1]: device-resident barrier sequence (used when seq == 0)
     using namespace mmu;
     MMU_CHECK_ARG(peer_params && peer_grads && peer_flags && m && v && state && done_counter, "mmu_epoch_tail_peer: null pointer");
     MMU_CHECK_ARG(world >= 1 && world <= MMU_PEER_MAX && rank >= 0 && rank < world, "mmu_epoch_tail_peer: bad world/rank");
@@ -290,14 +295,16 @@ extern "C" int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *
     if (sms <= 0) sms = 148;
     int64_t want = (hi4 - lo4 + 255) / 256;
     if (want < 1) want = 1;
-    const unsigned blocks = (unsigned)(want < (int64_t)sms ? want : (int64_t)sms);     // one wave: block 0 spins on the others
+    // peer accesses have microseconds of latency: as many threads in flight as the shard has 16-byte elements, up to 8
+    // blocks per SM (block 0 spins on the others' completion counter at the end; none of them waits for block 0)
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     const float4 *mcp = reinterpret_cast<const float4 *>(mc_params), *mcg = reinterpret_cast<const float4 *>(mc_grads);
     OptState *os = reinterpret_cast<OptState *>(state);
     cudaStream_t st = as_stream(stream);
 #define MMU_TAIL(MCV, WTV)                                                                                          \
     epoch_tail_peer_kernel<MCV, WTV><<<blocks, 256, 0, st>>>(pp, gg, ff, mcp, mcg, m, v, lo4, hi4, world, rank, seq, lr, beta1, \
                                                              beta2, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),  \
-                                                             (float)eps, os, done_counter)
+                                                             (float)eps, os, done_counter, done_counter + 1)
     if (mc_params) MMU_TAIL(true, 0);
     else if (world == 2) MMU_TAIL(false, 2);
     else if (world == 4) MMU_TAIL(false, 4);

@@ -246,7 +246,7 @@ class LayoutOptimizer:
                   "params": arr(*bases), "grads": arr(*[b + 4 * cap for b in bases]),
                   "flags": arr(*[b + 8 * cap for b in bases]),
                   "mc_params": mc, "mc_grads": (mc + 4 * cap) if mc else 0,
-                  "done": torch.zeros(1, dtype=torch.int32, device=dev)}
+                  "done": torch.zeros(2, dtype=torch.int32, device=dev)}
             _PEER_CACHE["buf"] = pr
         sym, cap = pr["sym"], pr["cap"]
         # the previous user's last epoch ended with the slot-1 barrier: no peer still reads these buffers
@@ -288,7 +288,7 @@ class LayoutOptimizer:
             return
         tail = mod.ref if self.mode == "transform" else mod.p
         grad_tail = None if self.mode == "transform" else mod.g
-        if profiler.enabled():
+        if profiler.enabled() and not getattr(self, "_capturing", False):
             # per kept edge (2+R) row reads of d*4 B and as many row accumulations in fit mode
             # (one, the query row, in transform mode), + 12 B of edge indices
             rows_touched = (2 + self.num_rep) * 2 if grad_tail is not None else (2 + self.num_rep) + 1
@@ -374,9 +374,11 @@ class LayoutOptimizer:
             pr["seq"] += 1
             if os.environ.get("MMUMAP_PEER_TAIL", "fused") == "fused":
                 # ONE launch: barrier + shard reduce + Adam + replica store + gradient clear + barrier + state advance
+                # (barrier sequence number on the device, pr["done"][1]: no per-epoch argument -> graph replayable;
+                #  pr["seq"] mirrors it on the host for the legacy barrier calls)
                 with profiler.stage("epoch_tail", level=2):
                     check(lib().mmu_epoch_tail_peer(pr["params"], pr["grads"], pr["flags"], pr["mc_params"], pr["mc_grads"],
-                                                    ptr(m), ptr(v), self.total, w, r, pr["seq"], self.lr, BETA1, BETA2, EPS,
+                                                    ptr(m), ptr(v), self.total, w, r, 0, self.lr, BETA1, BETA2, EPS,
                                                     ptr(self.state), ptr(pr["done"]), stream()), "mmu_epoch_tail_peer")
                 self.done += 1
                 if self.loss is not None:
@@ -472,6 +474,78 @@ class LayoutOptimizer:
                 stepped.record(main)
         main.wait_stream(side)
 
+    def _run_graphed(self, epochs: int):
+        """Multi-GPU (fused peer epoch tail), device sample stream: at 8 GPUs an epoch of BASELINE.json configs[1] is ~65 us
+        of GPU time but ~8 launches + 6 event operations of host time -- the host, not the GPU, sets the pace.  The whole
+        epoch {InfoNCE and the NEXT epoch's sampling on a forked branch | this epoch's force kernels} -> fused tail is
+        therefore captured ONCE per kept-list parity (the lists are double buffered) into two CUDA graphs and replayed:
+        one graph launch per epoch.  Every per-epoch scalar lives on the device (epoch counter and Adam step in the
+        optimiser state, the barrier sequence beside the completion counter), so the graphs have no arguments."""
+        eager = 2
+        self._run_overlapped(eager)                               # loads every kernel before capture, advances the state
+        epochs -= eager
+        main = torch.cuda.current_stream()
+        cap = torch.cuda.Stream()
+        side = torch.cuda.Stream()
+        bufs = []
+        for mod in self.mods:
+            bufs.append([(mod.kept_rec, mod.kept_hdr, mod.batch_kept),
+                         (torch.empty_like(mod.kept_rec), mod._new_hdr(), torch.zeros_like(mod.batch_kept))])
+            mod.all_hdrs = list(getattr(mod, "all_hdrs", [])) + [b[1] for b in bufs[-1]]
+
+        def sample_into(b, epoch, st):
+            for mi, mod in enumerate(self.mods):
+                g = mod.graph
+                kp, kc, bk = bufs[mi][b]
+                check(lib().mmu_edge_sample_at(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
+                                               mod.n_batches, mod.seed, epoch, ptr(self.state), ptr(kp), ptr(kc), ptr(bk), st),
+                      "mmu_edge_sample_at")
+
+        sample_into(0, self.done, main.cuda_stream)               # the first graphed epoch's list, explicit epoch number
+        fit_nce = self.mode == "fit" and len(self.mods) > 1
+        graphs, per_epoch = [], 0
+        cap.wait_stream(main)
+        side.wait_stream(main)
+        self._capturing = True
+        try:
+            for b in (0, 1):
+                gph = torch.cuda.CUDAGraph()
+                before = lib().mmu_launch_count()
+                with torch.cuda.stream(cap):
+                    gph.capture_begin()
+                    try:
+                        fork = torch.cuda.Event()
+                        fork.record(cap)
+                        side.wait_event(fork)
+                        with torch.cuda.stream(side):
+                            if fit_nce:
+                                self._infonce_all(side.cuda_stream)
+                            sample_into(b ^ 1, -2, side.cuda_stream)          # next epoch = device counter + 1
+                            join = torch.cuda.Event()
+                            join.record(side)
+                        for mi, mod in enumerate(self.mods):
+                            kp, kc, bk = bufs[mi][b]
+                            self._forces(mod, kp, kc, None, bk)
+                        cap.wait_event(join)
+                        self._adam_tail()
+                    finally:
+                        gph.capture_end()
+                per_epoch = lib().mmu_launch_count() - before
+                self.done -= 1                                    # the capture pass counted itself without executing
+                self.peer["seq"] -= 1
+                graphs.append(gph)
+        finally:
+            self._capturing = False
+        main.wait_stream(cap)
+        for e in range(epochs):
+            graphs[e & 1].replay()
+        lib().mmu_launch_count_add(max(epochs - 2, 0) * per_epoch)    # the two capture passes counted themselves once
+        self.done += epochs
+        self.peer["seq"] += epochs
+        for mi, mod in enumerate(self.mods):
+            mod.kept_hdr = bufs[mi][(epochs - 1) & 1][1] if epochs > 0 else mod.kept_hdr
+        self._graphs = graphs                                     # keep alive until the stream has drained
+
     def run(self, epochs: int):
         """`epochs` optimiser epochs.  With the device sample stream an epoch is a fixed sequence of
         launches whose only varying inputs (epoch counter, Adam step) live in device memory, so it
@@ -482,6 +556,13 @@ class LayoutOptimizer:
         use_graph = (self.sample_stream == "device" and self.loss is None and epochs > 2
                      and (mode == "1" or (mode == "auto" and small))
                      and (D.world() == 1 or (self.peer is None and os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1")))
+        peer_graph = (self.peer is not None and self.sample_stream == "device" and self.loss is None and epochs >= 12
+                      and self.mode in ("fit", "transform") and not profiler.enabled(2)
+                      and os.environ.get("MMUMAP_PEER_TAIL", "fused") == "fused"
+                      and os.environ.get("MMUMAP_EPOCH_GRAPH", "1") == "1")
+        if peer_graph:
+            self._run_graphed(epochs)
+            return self.result()
         if not use_graph:
             overlap = (self.sample_stream == "device" and self.mode in ("fit", "transform")
                        and epochs > 1 and os.environ.get("MMUMAP_OVERLAP_SAMPLE", "1") == "1")
