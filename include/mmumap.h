@@ -57,6 +57,7 @@ int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
  *   "knn_window_mb" (env MMUMAP_KNN_WINDOW_MB,  default -1) -1 = automatic, 0 = one launch, >0 = database window size
  *   "sgd_window_mb" (env MMUMAP_SGD_WINDOW_MB,  default -1) host hint for mmu_edge_forces' window_rows (-1 = automatic)
  *   "knn_fold_norms" (env MMUMAP_KNN_FOLD_NORMS, default 1) 0 = add |Y|^2 in the epilogue instead of inside the contraction
+ *   "tail_blocks_per_sm" (env MMUMAP_TAIL_BLOCKS_PER_SM, default 1) grid of mmu_epoch_tail_peer in blocks per SM
  * Unknown names return MMU_ERR_ARG. */
 int mmu_set_option(const char *name, int64_t value);
 int mmu_get_option(const char *name, int64_t *value);
@@ -118,6 +119,31 @@ int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_d
                int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
                int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
                float *out_dist, int32_t *stats, int32_t *fallback_rows, mmu_stream_t stream);
+
+/* Staged / pruned form of mmu_knn_tc (same arguments, plus):
+ *   stages         bit mask 1 = prep (fp16 operand copies, norms), 2 = candidates (tcgen05 kernel), 4 = certify + rescore;
+ *                  mmu_knn_tc is stages = 7.  The stages of one search share `workspace`.
+ *   qb_tile_begin / qb_tile_end [n_qblocks]   every 128-row query block searches only the 256-row database tiles
+ *                  [begin, end) -- or
+ *   tile_ptr [n_qblocks + 1] / tile_list      the tiles tile_list[tile_ptr[qb] .. tile_ptr[qb+1]) (no tile twice).
+ *   resume         1 = continue the per-row candidate lists an earlier candidates stage left in the workspace.
+ *   db_gid [n_db]  the database is a RE-ORDERED copy (cluster sorted): db_gid[j] is the original index of its row j; it is
+ *                  what out_idx reports and what ties and self exclusion (against query_gid) are decided on.
+ * This is the exact pruned search of umap_b200/knn_pruned.py: rows sorted by cluster, pass 1 over the home clusters'
+ * tiles, ball bounds |c_a - c_b| - r_block - R_b against the pass-1 k-th distance select the tiles of pass 2, and the
+ * usual certification + canonical fp32 rescoring finishes; a row is exact because every tile NOT visited is farther
+ * than its k-th neighbour by the triangle inequality.  Needs a single database split (min_splits = 0 on large inputs).
+ * mmu_knn_tc_layout: byte offsets inside the workspace {prm (scale at float 0, max |Y|^2 bits at word 1), |X|^2, |Y|^2,
+ * cand_idx, cand_score, tau} and {n_qblocks, n_splits, n_tiles, candidates per split, query-block rows, tile rows} in
+ * out_words[12]; the error-bound constants {c_rel, c_norm, c_abs, gamma} of the certification in out_consts[4]. */
+int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
+                  int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
+                  int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
+                  float *out_dist, int32_t *stats, int32_t *fallback_rows, int stages,
+                  const int32_t *qb_tile_begin, const int32_t *qb_tile_end, const int32_t *tile_ptr,
+                  const int32_t *tile_list, int resume, const int32_t *db_gid, mmu_stream_t stream);
+int mmu_knn_tc_layout(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits, int precision,
+                      int64_t *out_words, float *out_consts);
 
 /* K3: merge two sorted per-row lists (e.g. from two db shards) into one sorted top-k. */
 int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_b,

@@ -60,6 +60,7 @@ static OptionEntry g_options[OPT_COUNT] = {
     {"knn_window_mb", "MMUMAP_KNN_WINDOW_MB", -1},     // -1: automatic, 0: one launch, >0: window size for every pair launch
     {"sgd_window_mb", "MMUMAP_SGD_WINDOW_MB", -1},     // -1: automatic (tables beyond L2), 0: never, >0: p+g bytes per tail window
     {"knn_fold_norms", "MMUMAP_KNN_FOLD_NORMS", 1},    // 1: |Y|^2 and -2 folded into the contraction where supported
+    {"tail_blocks_per_sm", "MMUMAP_TAIL_BLOCKS_PER_SM", 1},   // grid of the fused multi-GPU epoch tail, blocks per SM
 };
 struct OptionInit {
     OptionInit() {

@@ -334,6 +334,12 @@ struct TcParams {
     int32_t *cand_idx;       // [n_qblocks][n_splits][TC_KP][128]
     float *cand_score;       // same layout
     float *tau;              // [n_qblocks][n_splits][TC_EPI_GROUPS][128]
+    // pruned search (single-CTA form, one split): every query block walks its OWN set of database tiles --
+    // a contiguous range [qb_tile_begin[qb], qb_tile_end[qb]) or the list tile_list[tile_ptr[qb] .. tile_ptr[qb+1])
+    const int32_t *qb_tile_begin;
+    const int32_t *qb_tile_end;
+    const int32_t *tile_ptr;
+    const int32_t *tile_list;
 };
 
 // NCTA = 1: one CTA per query block.  NCTA = 2: clusters of two CTAs along the query-block axis of the grid; the pair
@@ -371,8 +377,17 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     const int qblock = !p.split_major ? blockIdx.x : NCTA == 2 ? 2 * blockIdx.y + (blockIdx.x & 1) : blockIdx.y;
     const int split = !p.split_major ? blockIdx.y : NCTA == 2 ? (blockIdx.x >> 1) : blockIdx.x;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();   // swizzle atoms need 1024-byte alignment
-    const int t0 = split * p.tiles_per_split + p.window_begin;
-    const int t1 = min(min(p.n_tiles, (split + 1) * p.tiles_per_split), t0 + p.window_tiles);
+    int t0 = split * p.tiles_per_split + p.window_begin;
+    int t1 = min(min(p.n_tiles, (split + 1) * p.tiles_per_split), t0 + p.window_tiles);
+    const int32_t *my_list = nullptr;
+    if (p.tile_list) {
+        const int a = qblock < p.n_qblocks ? p.tile_ptr[qblock] : 0, b = qblock < p.n_qblocks ? p.tile_ptr[qblock + 1] : 0;
+        my_list = p.tile_list + a;
+        t0 = 0; t1 = b - a;
+    } else if (p.qb_tile_begin) {
+        t0 = qblock < p.n_qblocks ? p.qb_tile_begin[qblock] : 0;
+        t1 = qblock < p.n_qblocks ? p.qb_tile_end[qblock] : 0;
+    }
     const int n_my_tiles = max(0, t1 - t0);
 
     if (warp == 0 && lane == 0) {
@@ -406,7 +421,8 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = t0; t < t1; ++t) {
+            for (int ti = t0; ti < t1; ++ti) {
+                const int t = my_list ? my_list[ti] : ti;
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *a_dst = stage_base + stage * STAGE_BYTES;
@@ -490,7 +506,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         constexpr int COLS = TC_BN / TC_EPI_GROUPS;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int acc = it & 1;
-            const int n0 = (t0 + it) * TC_BN + grp * COLS;
+            const int n0 = (my_list ? my_list[it] : t0 + it) * TC_BN + grp * COLS;
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN + grp * COLS;
@@ -560,6 +576,8 @@ struct RsParams {
     int dim, k, exclude_self;
     int64_t query_index_base;
     const int32_t *query_gid;   // nullable: db index of query row q (self exclusion for gathered query rows)
+    const int32_t *db_gid;      // nullable: index REPORTED (and used for ties / self exclusion) for db row j -- the database was
+                                // re-ordered (cluster sorted) and db_gid maps a row of the re-ordered copy to its original index
     const float *xnorm;      // [n_query_pad] |X_q|^2 (centred, scaled)
     const uint32_t *prm;     // prm[1] = largest |Y|^2 bits
     int n_splits;
@@ -617,8 +635,9 @@ knn_tc_rescore_kernel(const RsParams p) {
         if (e < n_cand) {
             int32_t j = p.cand_idx[base + (int64_t)e * TC_BM + r];
             float s = p.cand_score[base + (int64_t)e * TC_BM + r];
-            bool self = p.exclude_self && (int64_t)j == qglob;
-            if (j >= 0 && j < p.n_db && !self) { cs[u] = s; ci[u] = j; }
+            const bool in = j >= 0 && j < p.n_db;
+            bool self = p.exclude_self && in && (int64_t)(p.db_gid ? p.db_gid[j] : j) == qglob;
+            if (in && !self) { cs[u] = s; ci[u] = j; }
         }
     }
     for (int s = lane; s < p.n_splits * TC_EPI_GROUPS; s += 32)
@@ -762,7 +781,7 @@ knn_tc_rescore_kernel(const RsParams p) {
                 }
             }
         }
-        if (my_j >= 0) keys[g] = dist_key(sqrtf(acc), my_j);
+        if (my_j >= 0) keys[g] = dist_key(sqrtf(acc), p.db_gid ? p.db_gid[my_j] : my_j);
     }
     // rank by counting; keys are distinct (distinct indices)
 #pragma unroll
@@ -880,19 +899,61 @@ extern "C" size_t mmu_knn_tc_workspace_bytes(int64_t n_query, int64_t n_db, int 
     return mmu::tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0).total;
 }
 
+static void tc_error_constants(int dim, int dim_pad, int width, int split, float *c_rel, float *c_norm, float *c_abs, float *gamma) {
+    // fp16 rounding of both operands (2 * 2^-11 on each product, x2 for the -2 factor, 1% headroom) plus
+    // the fp32 accumulation across dim_pad/16 MMAs and the final fma
+    *c_rel = 1.01f * 0x1p-9f + ((float)(dim_pad / 16) + 16.f) * 0x1p-22f;
+    if (split)   // hi+lo of each operand is exact to 2^-22 relative, the dropped lo.lo term is <= 2^-22 |x||y|; x2 for -2
+        *c_rel = 7.0f * 0x1p-22f + ((float)(width / 16) + 16.f) * 0x1p-22f;
+    // components below the fp16 subnormal spacing: <= 2^-25 absolute per element and operand, scaled values <= 2^14
+    *c_abs = (float)dim * 0x1p-9f;
+    *c_norm = ((float)(dim_pad / 32) + 8.f) * 0x1p-23f;      // lane-strided fma chain + warp tree + final fma
+    *gamma = ((float)dim + 4.f) * 0x1p-24f;
+}
+
+extern "C" int mmu_knn_tc_layout(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits, int precision,
+                                 int64_t *out_words, float *out_consts) {
+    using namespace mmu;
+    MMU_CHECK_ARG(out_words && out_consts && n_query > 0 && n_db > 0 && dim > 0, "mmu_knn_tc_layout: bad arguments");
+    const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0);
+    out_words[0] = (int64_t)L.off_prm;     out_words[1] = (int64_t)(L.shared_operand ? L.off_ynorm : L.off_xnorm);
+    out_words[2] = (int64_t)L.off_ynorm;   out_words[3] = (int64_t)L.off_cidx;
+    out_words[4] = (int64_t)L.off_cscore;  out_words[5] = (int64_t)L.off_tau;
+    out_words[6] = L.n_qblocks;            out_words[7] = L.n_splits;
+    out_words[8] = L.n_tiles;              out_words[9] = TC_KP;
+    out_words[10] = TC_BM;                 out_words[11] = TC_BN;
+    tc_error_constants(dim, L.dim_pad, L.width, precision != 0, &out_consts[0], &out_consts[1], &out_consts[2], &out_consts[3]);
+    return MMU_OK;
+}
+
 extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
                           int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
                           int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
                           float *out_dist, int32_t *stats, int32_t *fallback_rows, mmu_stream_t stream) {
+    return mmu_knn_tc_ex(query, n_query, db, n_db, dim, k, exclude_self, query_index_base, query_gid, query_is_db, min_splits,
+                         precision, workspace, workspace_bytes, out_idx, out_dist, stats, fallback_rows, 7, nullptr, nullptr,
+                         nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *db, int64_t n_db, int dim, int k,
+                             int exclude_self, int64_t query_index_base, const int32_t *query_gid, int query_is_db,
+                             int min_splits, int precision, void *workspace, size_t workspace_bytes, int32_t *out_idx,
+                             float *out_dist, int32_t *stats, int32_t *fallback_rows, int stages,
+                             const int32_t *qb_tile_begin, const int32_t *qb_tile_end, const int32_t *tile_ptr,
+                             const int32_t *tile_list, int resume, const int32_t *db_gid, mmu_stream_t stream) {
     using namespace mmu;
     MMU_CHECK_ARG(query && db && workspace && out_idx && out_dist && stats && fallback_rows, "mmu_knn_tc: null pointer");
+    MMU_CHECK_ARG(stages >= 1 && stages <= 7, "mmu_knn_tc_ex: stages must be a mask of 1 (prep) | 2 (candidates) | 4 (rescore)");
+    MMU_CHECK_ARG((qb_tile_begin == nullptr) == (qb_tile_end == nullptr) && (tile_ptr == nullptr) == (tile_list == nullptr),
+                  "mmu_knn_tc_ex: tile ranges / tile lists come in pairs");
+    const bool pruned = qb_tile_begin || tile_list;
     MMU_CHECK_ARG(k >= 1 && k <= MMU_KNN_TC_MAX_K, "mmu_knn_tc: k=%d outside [1,%d]", k, MMU_KNN_TC_MAX_K);
     MMU_CHECK_ARG(dim >= 1 && n_db >= 1 && n_query >= 0, "mmu_knn_tc: bad sizes");
     MMU_CHECK_ARG(n_db < (int64_t)2147483647 - TC_BN, "mmu_knn_tc: db index exceeds int32");
     MMU_CHECK_ARG(!query_is_db || (query == db && n_query == n_db && query_index_base == 0),
                   "mmu_knn_tc: query_is_db requires identical query and db");
     cudaStream_t st = as_stream(stream);
-    MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
+    if (stages & 4) MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
     if (n_query == 0) return MMU_OK;
     MMU_CHECK_ARG(min_splits >= 0 && min_splits <= 8, "mmu_knn_tc: min_splits outside [0,8]");
     MMU_CHECK_ARG(precision == 0 || precision == 1, "mmu_knn_tc: precision must be 0 (fp16) or 1 (split fp16)");
@@ -912,6 +973,8 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     float *cscore = reinterpret_cast<float *>(ws + L.off_cscore);
     float *tau = reinterpret_cast<float *>(ws + L.off_tau);
 
+    MMU_CHECK_ARG(!pruned || L.n_splits == 1, "mmu_knn_tc_ex: per-block tile sets need a single database split (got %d)", L.n_splits);
+    if (stages & 1) {
     // ---- prep
     MMU_CUDA(cudaMemsetAsync(prm, 0, 256, st));
     tc_colsum_kernel<<<L.stat_blocks, 256, 0, st>>>(db, n_db, dim, L.rows_per_stat_block, partial, prm + 2);
@@ -937,13 +1000,16 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         ++launches;
     }
     MMU_LAUNCH_CHECK_N(launches);
+    }
 
+    if (stages & 2) {
     // ---- candidates
     // CTA pairs (cta_group::2) for long rows; option knn_cta_pairs = 0 keeps one CTA per query block (A/B measurements)
     const int pairs_allowed = option(OPT_KNN_CTA_PAIRS) != 0;
     // Short rows (width < 512: at most 7 k-blocks per tile) are bound by the per-tile epilogue, not by operand
     // traffic; there a pair only couples the two epilogues (1M x 128, k = 30: 795 ms paired, 695 ms unpaired).
-    const int ncta = (pairs_allowed && L.n_qblocks >= 2 && L.width >= 512) ? 2 : 1;
+    // (per-block tile sets: the two CTAs of a pair would have to walk the same tiles, so the pruned search is single-CTA)
+    const int ncta = (pairs_allowed && !pruned && L.n_qblocks >= 2 && L.width >= 512) ? 2 : 1;
     CUtensorMap tm_q, tm_db;
     int rc = make_map(&tm_q, q16, L.q_pad, L.width, TC_BM);
     if (rc) return rc;
@@ -973,7 +1039,9 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
     }
     tp.window_begin = 0;
     tp.window_tiles = L.tiles_per_split;
-    tp.resume = 0;
+    tp.resume = resume ? 1 : 0;
+    tp.qb_tile_begin = qb_tile_begin; tp.qb_tile_end = qb_tile_end; tp.tile_ptr = tile_ptr; tp.tile_list = tile_list;
+    if (pruned) tp.split_major = 0;
     if (ncta == 2) {
         // Pairs do not stay in lock-step over a long database pass the way single CTAs do (traced on 1M x 768: the
         // spread of the CTAs' positions grows by ~0.2 ms per wave until every pair streams its tiles from DRAM,
@@ -1006,7 +1074,7 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         cfg.numAttrs = 1;
         for (int w0 = 0; w0 < L.tiles_per_split; w0 += tp.window_tiles) {
             tp.window_begin = w0;
-            tp.resume = w0 > 0;
+            tp.resume = (w0 > 0 || resume) ? 1 : 0;
             MMU_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_candidates_kernel<2>, tm_q, tm_db, tp));
             if (w0 > 0) mmu_launch_count_add(1);
         }
@@ -1014,23 +1082,20 @@ extern "C" int mmu_knn_tc(const float *query, int64_t n_query, const float *db, 
         const dim3 grid = tp.split_major ? dim3(L.n_splits, L.n_qblocks) : dim3(L.n_qblocks, L.n_splits);
         knn_tc_candidates_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, st>>>(tm_q, tm_db, tp);
     }
+    note_kernel(SITE_KNN_CANDIDATES, "knn_tc_candidates_kernel<%d>(%s%s, width %d, %d split%s)", ncta,
+                ncta == 2 ? "cta_group::2 pairs" : "cta_group::1", pruned ? ", per-block tile sets" : "", L.width, L.n_splits,
+                L.n_splits > 1 ? "s" : "");
     MMU_LAUNCH_CHECK();
+    }
 
+    if (!(stages & 4)) return MMU_OK;
     // ---- certify + rescore
     RsParams rp;
     rp.query = query; rp.db = db; rp.n_query = n_query; rp.n_db = n_db; rp.dim = dim; rp.k = k;
-    rp.exclude_self = exclude_self; rp.query_index_base = query_index_base; rp.query_gid = query_gid;
+    rp.exclude_self = exclude_self; rp.query_index_base = query_index_base; rp.query_gid = query_gid; rp.db_gid = db_gid;
     rp.xnorm = xnorm; rp.prm = prm; rp.n_splits = L.n_splits;
     rp.cand_idx = cidx; rp.cand_score = cscore; rp.tau = tau;
-    // fp16 rounding of both operands (2 * 2^-11 on each product, x2 for the -2 factor, 1% headroom) plus
-    // the fp32 accumulation across dim_pad/16 MMAs and the final fma
-    rp.c_rel = 1.01f * 0x1p-9f + ((float)(L.dim_pad / 16) + 16.f) * 0x1p-22f;
-    if (split)   // hi+lo of each operand is exact to 2^-22 relative, the dropped lo.lo term is <= 2^-22 |x||y|; x2 for -2
-        rp.c_rel = 7.0f * 0x1p-22f + ((float)(L.width / 16) + 16.f) * 0x1p-22f;
-    // components below the fp16 subnormal spacing: <= 2^-25 absolute per element and operand, scaled values <= 2^14
-    rp.c_abs = split ? (float)dim * 0x1p-9f : (float)dim * 0x1p-9f;
-    rp.c_norm = ((float)(L.dim_pad / 32) + 8.f) * 0x1p-23f;      // lane-strided fma chain + warp tree + final fma
-    rp.gamma = ((float)dim + 4.f) * 0x1p-24f;
+    tc_error_constants(dim, L.dim_pad, L.width, split, &rp.c_rel, &rp.c_norm, &rp.c_abs, &rp.gamma);
     rp.out_idx = out_idx; rp.out_dist = out_dist; rp.stats = stats; rp.fallback_rows = fallback_rows;
     unsigned rblocks = (unsigned)((n_query + RS_WARPS - 1) / RS_WARPS);
     bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0);

@@ -297,7 +297,9 @@ extern "C" int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *
     if (want < 1) want = 1;
     // peer accesses have microseconds of latency: as many threads in flight as the shard has 16-byte elements, up to 8
     // blocks per SM (block 0 spins on the others' completion counter at the end; none of them waits for block 0)
-    const unsigned blocks = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    long long per_sm = option(OPT_TAIL_BLOCKS_PER_SM);
+    if (per_sm < 1) per_sm = 1;
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     const float4 *mcp = reinterpret_cast<const float4 *>(mc_params), *mcg = reinterpret_cast<const float4 *>(mc_grads);
     OptState *os = reinterpret_cast<OptState *>(state);
     cudaStream_t st = as_stream(stream);

@@ -1,0 +1,228 @@
+"""Exact kNN with cluster pruning for large, low-dimensional, clustered inputs (BASELINE.json configs[3]: 10M x 128).
+
+Role of /root/reference/impl/model.py:81-195 (candidate search + per-row top-k), same result contract as
+knn_tc.knn_tc: indices and fp32 distance bit patterns of the exhaustive search.  On data of this kind the dense
+contraction is the wrong algorithm at full size -- 10^14 distances of which all but a sliver are between points of
+different clusters -- so the database is re-ordered by cluster and every 128-row query block searches only the 256-row
+tiles that can hold one of its neighbours:
+
+  1. centroids: farthest-point sampling on a strided subsample (every cluster of the data gets one);
+  2. assignment: each row's nearest centroid and its fp32 distance to it, with the engine's own kNN kernel (k = 1);
+  3. rows sorted by cluster (`perm`), cluster radius R_b = largest member distance;
+  4. pass 1 (mmu_knn_tc_ex, per-block tile RANGE): every query block searches the tiles of its own cluster(s);
+  5. bound: U = the block's largest (k+1)-th smallest approximate score + error bound >= every row's true k-th
+     neighbour distance (squared); a cluster b must still be searched iff
+         |c_a - c_b| - rho_block - R_b  <  sqrt(U)          (triangle inequality; rho_block = largest |x - c_a| in the block)
+  6. pass 2 (per-block tile LIST, candidate lists resumed): the tiles of those clusters not yet visited;
+  7. the usual certification + canonical fp32 rescoring, reporting ORIGINAL indices (db_gid = perm), so ties and self
+     exclusion are decided exactly as in the unpruned search.
+
+A row is exact because (a) inside the visited tiles the certification of knn_tc.cu holds unchanged and (b) every point of
+an unvisited tile is farther than the row's k-th neighbour by the bound of step 5 (taken with a 1e-3 relative safety
+margin against the fp32 rounding of the centroid distances and radii).  Rows the certification rejects go through the
+same second level / exhaustive fallback as in knn_tc.knn_tc.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+
+import torch
+
+from . import dist as D
+from . import native
+from .native import check, lib, ptr, stream
+
+last_stats: dict = {}
+SAFETY = 1e-3
+
+
+def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
+    """median k-th neighbour distance of a strided row sample / median distance between random rows: small when the
+    data is clustered at the scale of its neighbourhoods, i.e. when ball bounds can prune."""
+    from .knn_tc import _call
+    n = x.shape[0]
+    rows = torch.arange(0, n, max(1, n // sample), device=x.device, dtype=torch.int64)[:sample]
+    _, dist, st, _ = _call(x.index_select(0, rows), x, k, True, 0, rows.to(torch.int32), False, 0, 1)
+    ok = torch.isfinite(dist[:, k - 1]) & (dist[:, k - 1] > 0)
+    if int(ok.sum()) < sample // 2:
+        return 1.0
+    dk = dist[ok, k - 1].median()
+    other = x.index_select(0, (rows * 7919 + 13) % n)
+    dr = (x.index_select(0, rows) - other).norm(dim=1).median()
+    return float((dk / dr.clamp(min=1e-30)).item())
+
+
+def farthest_point_centroids(x: torch.Tensor, n_centroids: int, sub_rows: int = 65536) -> torch.Tensor:
+    """Greedy k-centre on a strided subsample: deterministic (no RNG: every rank gets the same centroids)."""
+    n = x.shape[0]
+    sub = x[:: max(1, n // sub_rows)][:sub_rows].contiguous()
+    d2 = torch.full((sub.shape[0],), float("inf"), device=x.device)
+    cent = torch.empty((n_centroids, x.shape[1]), dtype=torch.float32, device=x.device)
+    i = torch.zeros((), dtype=torch.int64, device=x.device)
+    for c in range(n_centroids):
+        row = sub.index_select(0, i.reshape(1))
+        cent[c] = row[0]
+        d2 = torch.minimum(d2, (sub - row).square().sum(dim=1))
+        i = d2.argmax()
+    return cent
+
+
+def _views(ws: torch.Tensor, words, n_rows_pad: int):
+    off_prm, off_xnorm, _, _, off_cscore, _, n_qb, n_splits, _, kp, bm, _ = words
+    prm = ws[off_prm:off_prm + 16].view(torch.float32)
+    xnorm = ws[off_xnorm:off_xnorm + 4 * n_qb * bm].view(torch.float32)
+    cscore = ws[off_cscore:off_cscore + 4 * n_qb * n_splits * kp * bm].view(torch.float32).view(n_qb, n_splits * kp, bm)
+    return prm, xnorm, cscore
+
+
+def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_fraction: float = 0.5):
+    """Exact kNN of every row of `x` among the rows of `x` (self excluded).  Returns (idx int32 [N,k], dist float32 [N,k],
+    fallback_rows int64 [F]) with the rows of `fallback_rows` NOT filled in (the caller runs them through the deeper
+    levels of knn_tc), or None when the tile lists show that pruning does not pay (the caller runs the full search)."""
+    from . import graph as G
+    native.require_cuda()
+    L = lib()
+    st = stream()
+    dev = x.device
+    n, dim = x.shape
+    world, rank = D.world(), D.rank()
+    if n_centroids is None:
+        n_centroids = int(min(8192, max(256, 2 ** round(math.log2(1.3 * math.sqrt(n))))))
+    # ---- 1-3: centroids, assignment, cluster order
+    cent = farthest_point_centroids(x, n_centroids)
+    a_idx, a_dist = G.knn_graph(x, cent, 1, exclude_self=False, method="tc")
+    a_idx = a_idx[:, 0].long()
+    a_dist = a_dist[:, 0]
+    perm = torch.argsort(a_idx, stable=True)
+    assign = a_idx.index_select(0, perm)
+    counts = torch.bincount(a_idx, minlength=n_centroids)
+    ends = torch.cumsum(counts, 0)
+    starts = ends - counts
+    radius = torch.zeros(n_centroids, device=dev).scatter_reduce(0, a_idx, a_dist, reduce="amax", include_self=True)
+    xs = x.index_select(0, perm)
+    perm32 = perm.to(torch.int32)
+    # ---- query rows of this rank: a block of whole 128-row query blocks of the SORTED order
+    q_lo, q_hi = D.row_block(n, rank, world) if world > 1 else (0, n)
+    xq = xs if world == 1 else xs[q_lo:q_hi].contiguous()
+    gq = perm32 if world == 1 else perm32[q_lo:q_hi].contiguous()
+    nq = xq.shape[0]
+    same = world == 1
+    precision = 1                      # split-fp16 operands: after pruning the contraction is cheap, certification is not
+    ws_bytes = L.mmu_knn_tc_workspace_bytes(nq, n, dim, int(same), 0, precision)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    words = (ctypes.c_int64 * 12)()
+    consts = (ctypes.c_float * 4)()
+    check(L.mmu_knn_tc_layout(nq, n, dim, int(same), 0, precision, words, consts), "mmu_knn_tc_layout")
+    words = list(words)
+    n_qb, n_splits, n_tiles, kp, bm, bn = words[6], words[7], words[8], words[9], words[10], words[11]
+    if n_splits != 1 or k + 1 > kp:
+        return None
+    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int32, device=dev)
+    fallback = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
+
+    def stage(mask, tb=None, te=None, tp=None, tl=None, resume=0):
+        check(L.mmu_knn_tc_ex(ptr(xq), nq, ptr(xs), n, dim, k, 1, 0, ptr(gq), int(same), 0, precision, ptr(ws), ws_bytes,
+                              ptr(idx), ptr(dist), ptr(stats), ptr(fallback), mask, ptr(tb), ptr(te), ptr(tp), ptr(tl), resume,
+                              ptr(perm32), st), "mmu_knn_tc_ex")
+
+    stage(1)
+    # ---- 4: pass 1 over the home clusters' tiles (one contiguous range per query block)
+    first = torch.arange(n_qb, device=dev, dtype=torch.int64) * bm + q_lo
+    last = torch.clamp(first + bm, max=q_hi) - 1
+    a0 = assign.index_select(0, first)
+    a1 = assign.index_select(0, last)
+    t_begin = (starts.index_select(0, a0) // bn).to(torch.int32)
+    t_end = ((ends.index_select(0, a1) + bn - 1) // bn).to(torch.int32)
+    stage(2, tb=t_begin, te=t_end)
+    # ---- 5: bound.  U (scaled, squared) >= true k-th neighbour distance of every row of the block
+    prm, xnorm, cscore = _views(ws, words, nq)
+    scale = prm[0]
+    ymax2 = prm[1:2].view(torch.int32).view(torch.float32)[0] if False else ws[words[0] + 4: words[0] + 8].view(torch.float32)[0]
+    c_rel, c_norm, c_abs, _ = (float(v) for v in consts)
+    kth = torch.kthvalue(cscore, k + 1, dim=1).values                                  # [n_qb, 128]; +inf when the list is short
+    x2 = xnorm[: n_qb * bm].view(n_qb, bm)
+    eps = c_rel * x2.sqrt() * ymax2.sqrt() + c_norm * ymax2 + c_abs
+    u = (kth + eps + x2).clamp(min=0.0)
+    valid_row = (torch.arange(n_qb * bm, device=dev).view(n_qb, bm) + q_lo) < q_hi
+    u = torch.where(valid_row, u, torch.zeros_like(u))
+    r_k = u.amax(dim=1).sqrt() / scale                                                 # original units, per query block
+    # rho_block = largest |x - c_a0| over the block's rows
+    rho = torch.empty(n_qb, device=dev)
+    step = max(1, (1 << 28) // (bm * dim * 4))
+    for b0 in range(0, n_qb, step):
+        b1 = min(n_qb, b0 + step)
+        r0, r1 = b0 * bm, min(nq, b1 * bm)
+        blk = torch.zeros(((b1 - b0) * bm, dim), device=dev)
+        blk[: r1 - r0] = xq[r0:r1]
+        d = (blk.view(b1 - b0, bm, dim) - cent.index_select(0, a0[b0:b1])[:, None, :]).norm(dim=2)
+        vr = valid_row[b0:b1]
+        rho[b0:b1] = torch.where(vr, d, torch.zeros_like(d)).amax(dim=1)
+    cd = torch.cdist(cent, cent, compute_mode="donot_use_mm_for_euclid_dist")
+    nonempty = counts > 0
+    ts = (starts // bn).to(torch.int64)
+    te = torch.where(nonempty, (ends - 1) // bn, ts - 1).to(torch.int64)               # inclusive; empty cluster: no tiles
+    qb_ids, tile_ids = [], []
+    chunk = max(1, (1 << 26) // n_centroids)
+    for b0 in range(0, n_qb, chunk):
+        b1 = min(n_qb, b0 + chunk)
+        lb = cd.index_select(0, a0[b0:b1]) - rho[b0:b1, None] - radius[None, :]
+        need = (lb * (1.0 - SAFETY) <= r_k[b0:b1, None] * (1.0 + SAFETY)) & nonempty[None, :]
+        qb, cl = need.nonzero(as_tuple=True)
+        if qb.numel() == 0:
+            continue
+        cnt = (te[cl] - ts[cl] + 1)
+        rep_qb = torch.repeat_interleave(qb + b0, cnt)
+        base = torch.repeat_interleave(ts[cl], cnt)
+        offs = torch.arange(rep_qb.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        tl = base + offs
+        # clusters are visited in ascending order: a tile shared by two neighbouring clusters appears twice in a row
+        keep = torch.ones_like(tl, dtype=torch.bool)
+        keep[1:] = (tl[1:] != tl[:-1]) | (rep_qb[1:] != rep_qb[:-1])
+        keep &= (tl < t_begin[rep_qb].long()) | (tl >= t_end[rep_qb].long())            # pass 1 already searched these
+        qb_ids.append(rep_qb[keep])
+        tile_ids.append(tl[keep])
+    if qb_ids:
+        qb_all = torch.cat(qb_ids)
+        tiles_all = torch.cat(tile_ids).to(torch.int32)
+    else:
+        qb_all = torch.zeros(0, dtype=torch.int64, device=dev)
+        tiles_all = torch.zeros(0, dtype=torch.int32, device=dev)
+    per_block = torch.bincount(qb_all, minlength=n_qb)
+    tile_ptr = torch.zeros(n_qb + 1, dtype=torch.int32, device=dev)
+    tile_ptr[1:] = torch.cumsum(per_block, 0).to(torch.int32)
+    visited = int(tiles_all.numel()) + int((t_end - t_begin).sum().item())
+    fraction = visited / max(1, n_qb * n_tiles)
+    last_stats.clear()
+    last_stats.update(rows=n, centroids=n_centroids, query_blocks=n_qb, tiles=n_tiles, visited_tile_fraction=fraction,
+                      pass1_tiles=int((t_end - t_begin).sum().item()), pass2_tiles=int(tiles_all.numel()))
+    if fraction > max_fraction:
+        return None
+    # ---- 6: pass 2
+    if tiles_all.numel():
+        stage(2, tp=tile_ptr, tl=tiles_all.contiguous(), resume=1)
+    # ---- 7: certification + canonical fp32 rescoring, original indices
+    stage(4)
+    st_host = stats.tolist()
+    n_fb = int(st_host[0])
+    fb_sorted = fallback[:n_fb].long() + q_lo                                           # positions in the sorted order
+    # back to the caller's row order (multi-GPU: gather the ranks' blocks of the sorted order first)
+    if world > 1:
+        per = D.block_size(n, world)
+        idx = D.all_gather_rows(idx, n, per)
+        dist = D.all_gather_rows(dist, n, per)
+        fb_pad = torch.full((per,), -1, dtype=torch.int64, device=dev)
+        fb_pad[:n_fb] = fb_sorted
+        import torch.distributed as tdist
+        fb_all = torch.empty(world * per, dtype=torch.int64, device=dev)
+        tdist.all_gather_into_tensor(fb_all, fb_pad)
+        fb_sorted = fb_all[fb_all >= 0]
+    out_idx = torch.empty_like(idx)
+    out_dist = torch.empty_like(dist)
+    out_idx.index_copy_(0, perm, idx)
+    out_dist.index_copy_(0, perm, dist)
+    last_stats.update(uncertified_rows=int(fb_sorted.numel()), rescored_per_row=st_host[1] / max(st_host[2], 1))
+    return out_idx, out_dist, perm.index_select(0, fb_sorted)

@@ -411,8 +411,10 @@ class LayoutOptimizer:
         embeddings, so it runs on a second stream (double-buffered kept lists, explicit epoch number) while
         the force kernels of epoch e execute; the main stream only waits for the sampled-event."""
         main = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream()                 # InfoNCE beside the force kernels
+        samp = torch.cuda.Stream()                 # the next epoch's sampling (its own branch: not queued behind InfoNCE)
         side.wait_stream(main)
+        samp.wait_stream(main)
         dev = torch.device("cuda")
         bufs = []
         for mod in self.mods:
@@ -430,17 +432,17 @@ class LayoutOptimizer:
 
         def issue_sample(e):
             b = e & 1
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(samp):
                 if consumed[b] is not None:
-                    side.wait_event(consumed[b])
+                    samp.wait_event(consumed[b])
                 for mi, mod in enumerate(self.mods):
                     g = mod.graph
                     kp, kc, bk = bufs[mi][b]
                     check(lib().mmu_edge_sample_at(ptr(g.row), ptr(g.col), ptr(g.val), mod.e_lo, mod.e_hi, mod.batch_size,
                                                    mod.n_batches, mod.seed, base + e, ptr(self.state), ptr(kp), ptr(kc),
-                                                   ptr(bk), side.cuda_stream), "mmu_edge_sample_at")
+                                                   ptr(bk), samp.cuda_stream), "mmu_edge_sample_at")
                 ev = torch.cuda.Event()
-                ev.record(side)
+                ev.record(samp)
                 sampled[b] = ev
 
         issue_sample(0)
@@ -473,6 +475,7 @@ class LayoutOptimizer:
                 stepped = torch.cuda.Event()
                 stepped.record(main)
         main.wait_stream(side)
+        main.wait_stream(samp)
 
     def _run_graphed(self, epochs: int):
         """Multi-GPU (fused peer epoch tail), device sample stream: at 8 GPUs an epoch of BASELINE.json configs[1] is ~65 us
@@ -487,6 +490,7 @@ class LayoutOptimizer:
         main = torch.cuda.current_stream()
         cap = torch.cuda.Stream()
         side = torch.cuda.Stream()
+        samp = torch.cuda.Stream()
         bufs = []
         for mod in self.mods:
             bufs.append([(mod.kept_rec, mod.kept_hdr, mod.batch_kept),
@@ -506,6 +510,7 @@ class LayoutOptimizer:
         graphs, per_epoch = [], 0
         cap.wait_stream(main)
         side.wait_stream(main)
+        samp.wait_stream(main)
         self._capturing = True
         try:
             for b in (0, 1):
@@ -517,16 +522,21 @@ class LayoutOptimizer:
                         fork = torch.cuda.Event()
                         fork.record(cap)
                         side.wait_event(fork)
+                        samp.wait_event(fork)
                         with torch.cuda.stream(side):
                             if fit_nce:
                                 self._infonce_all(side.cuda_stream)
-                            sample_into(b ^ 1, -2, side.cuda_stream)          # next epoch = device counter + 1
                             join = torch.cuda.Event()
                             join.record(side)
+                        with torch.cuda.stream(samp):
+                            sample_into(b ^ 1, -2, samp.cuda_stream)          # next epoch = device counter + 1
+                            join2 = torch.cuda.Event()
+                            join2.record(samp)
                         for mi, mod in enumerate(self.mods):
                             kp, kc, bk = bufs[mi][b]
                             self._forces(mod, kp, kc, None, bk)
                         cap.wait_event(join)
+                        cap.wait_event(join2)
                         self._adam_tail()
                     finally:
                         gph.capture_end()

@@ -42,6 +42,10 @@ _SIGNATURES = {
     "mmu_knn_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "mmu_knn_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int,
                            c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmu_knn_tc_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int,
+                              c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int, c_void_p, c_void_p]),
+    "mmu_knn_tc_layout": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mmu_knn_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_smooth_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
