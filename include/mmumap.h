@@ -100,7 +100,7 @@ int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_
  * query_is_db != 0 (fit mode): query and db are the same array and share one fp16 copy.
  * out_idx holds db row numbers; exclude_self drops the pair j == query_index_base + q, or
  * j == query_gid[q] when query_gid (nullable, [n_query]) is given (gathered query rows).
- * min_splits (0..8, 0 = automatic): the database range is searched in at least that many splits,
+ * min_splits (0..8, 0 = automatic, -1 = exactly one): the database range is searched in at least that many splits,
  * each keeping its own 64 candidates per row -- a deeper candidate pool for rows whose
  * neighbourhood gaps are too small for one list to be certified (the host retries the rows of
  * fallback_rows with min_splits = 8 and precision = 1 before resorting to the exhaustive kernel).

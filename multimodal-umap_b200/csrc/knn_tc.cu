@@ -868,6 +868,7 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     // more splits = deeper candidate pool (64 per split): the caller raises min_splits for rows whose
     // neighbourhood gaps are too small for one list to certify
     if (min_splits > best_s) best_s = min_splits;
+    if (min_splits < 0) best_s = 1;                  // pinned to one split (per-block tile sets of the pruned search)
     if (best_s > 8) best_s = 8;
     if (best_s > L.n_tiles) best_s = L.n_tiles;
     L.n_splits = best_s;
@@ -955,7 +956,7 @@ extern "C" int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *d
     cudaStream_t st = as_stream(stream);
     if (stages & 4) MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
     if (n_query == 0) return MMU_OK;
-    MMU_CHECK_ARG(min_splits >= 0 && min_splits <= 8, "mmu_knn_tc: min_splits outside [0,8]");
+    MMU_CHECK_ARG(min_splits >= -1 && min_splits <= 8, "mmu_knn_tc: min_splits outside [-1,8]");
     MMU_CHECK_ARG(precision == 0 || precision == 1, "mmu_knn_tc: precision must be 0 (fp16) or 1 (split fp16)");
     const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0);
     const int split = precision != 0;

@@ -115,6 +115,13 @@ def knn_graph(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool,
         # multi-GPU fit: query row-blocks per rank, all-gather of the per-row results
         lo, hi = D.row_block(db.shape[0], D.rank(), D.world())
         with profiler.stage("knn", flops=2.0 * (hi - lo) * db.shape[0] * db.shape[1], kernel=kernel):
+            if use_tc and exclude_self:
+                # large clustered low-dimensional input: the cluster-pruned search, its query blocks sharded over the ranks
+                from . import knn_tc as KT
+                if KT.prune_applicable(db.shape[0], db.shape[1], k):
+                    res = KT.knn_tc(db, db, k, True, prune=True)
+                    if res is not None:
+                        return res
             if os.environ.get("MMUMAP_KNN_DIST", "rows") == "ring":      # default "rows": impl/model.py DEFAULT_KNN_DIST
                 # row-sharded DATABASE: each rank only touches its own rows of `db`; the shards rotate round
                 # the ranks peer-to-peer (NCCL send/recv over NVLink) under a running per-row top-k merge

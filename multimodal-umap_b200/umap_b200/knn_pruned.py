@@ -36,6 +36,7 @@ from .native import check, lib, ptr, stream
 
 last_stats: dict = {}
 SAFETY = 1e-3
+ONE_SPLIT = -1                 # min_splits value that pins the search to a single database split (one 64-entry list per row)
 
 
 def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
@@ -44,8 +45,10 @@ def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
     from .knn_tc import _call
     n = x.shape[0]
     rows = torch.arange(0, n, max(1, n // sample), device=x.device, dtype=torch.int64)[:sample]
-    _, dist, st, _ = _call(x.index_select(0, rows), x, k, True, 0, rows.to(torch.int32), False, 0, 1)
-    ok = torch.isfinite(dist[:, k - 1]) & (dist[:, k - 1] > 0)
+    _, dist, st, fb = _call(x.index_select(0, rows), x, k, True, 0, rows.to(torch.int32), False, 0, 1)
+    ok = torch.ones(rows.numel(), dtype=torch.bool, device=x.device)
+    ok[fb[: int(st[0])].long()] = False                     # uncertified rows are not written by the call
+    ok &= torch.isfinite(dist[:, k - 1]) & (dist[:, k - 1] > 0)
     if int(ok.sum()) < sample // 2:
         return 1.0
     dk = dist[ok, k - 1].median()
@@ -81,7 +84,6 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     """Exact kNN of every row of `x` among the rows of `x` (self excluded).  Returns (idx int32 [N,k], dist float32 [N,k],
     fallback_rows int64 [F]) with the rows of `fallback_rows` NOT filled in (the caller runs them through the deeper
     levels of knn_tc), or None when the tile lists show that pruning does not pay (the caller runs the full search)."""
-    from . import graph as G
     native.require_cuda()
     L = lib()
     st = stream()
@@ -92,7 +94,8 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
         n_centroids = int(min(8192, max(256, 2 ** round(math.log2(1.3 * math.sqrt(n))))))
     # ---- 1-3: centroids, assignment, cluster order
     cent = farthest_point_centroids(x, n_centroids)
-    a_idx, a_dist = G.knn_graph(x, cent, 1, exclude_self=False, method="tc")
+    from .knn_tc import knn_tc
+    a_idx, a_dist = knn_tc(x, cent, 1, False)               # nearest centroid and the canonical fp32 distance to it
     a_idx = a_idx[:, 0].long()
     a_dist = a_dist[:, 0]
     perm = torch.argsort(a_idx, stable=True)
@@ -110,11 +113,11 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     nq = xq.shape[0]
     same = world == 1
     precision = 1                      # split-fp16 operands: after pruning the contraction is cheap, certification is not
-    ws_bytes = L.mmu_knn_tc_workspace_bytes(nq, n, dim, int(same), 0, precision)
+    ws_bytes = L.mmu_knn_tc_workspace_bytes(nq, n, dim, int(same), ONE_SPLIT, precision)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     words = (ctypes.c_int64 * 12)()
     consts = (ctypes.c_float * 4)()
-    check(L.mmu_knn_tc_layout(nq, n, dim, int(same), 0, precision, words, consts), "mmu_knn_tc_layout")
+    check(L.mmu_knn_tc_layout(nq, n, dim, int(same), ONE_SPLIT, precision, words, consts), "mmu_knn_tc_layout")
     words = list(words)
     n_qb, n_splits, n_tiles, kp, bm, bn = words[6], words[7], words[8], words[9], words[10], words[11]
     if n_splits != 1 or k + 1 > kp:
@@ -125,7 +128,7 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     fallback = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
 
     def stage(mask, tb=None, te=None, tp=None, tl=None, resume=0):
-        check(L.mmu_knn_tc_ex(ptr(xq), nq, ptr(xs), n, dim, k, 1, 0, ptr(gq), int(same), 0, precision, ptr(ws), ws_bytes,
+        check(L.mmu_knn_tc_ex(ptr(xq), nq, ptr(xs), n, dim, k, 1, 0, ptr(gq), int(same), ONE_SPLIT, precision, ptr(ws), ws_bytes,
                               ptr(idx), ptr(dist), ptr(stats), ptr(fallback), mask, ptr(tb), ptr(te), ptr(tp), ptr(tl), resume,
                               ptr(perm32), st), "mmu_knn_tc_ex")
 
@@ -141,7 +144,7 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     # ---- 5: bound.  U (scaled, squared) >= true k-th neighbour distance of every row of the block
     prm, xnorm, cscore = _views(ws, words, nq)
     scale = prm[0]
-    ymax2 = prm[1:2].view(torch.int32).view(torch.float32)[0] if False else ws[words[0] + 4: words[0] + 8].view(torch.float32)[0]
+    ymax2 = prm[1]                                           # largest |Y|^2 of the scaled database (float bits)
     c_rel, c_norm, c_abs, _ = (float(v) for v in consts)
     kth = torch.kthvalue(cscore, k + 1, dim=1).values                                  # [n_qb, 128]; +inf when the list is short
     x2 = xnorm[: n_qb * bm].view(n_qb, bm)

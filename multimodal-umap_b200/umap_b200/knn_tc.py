@@ -17,6 +17,15 @@ from .native import check, lib, ptr, stream
 
 last_stats: dict = {}
 DEEP_SPLITS = 8
+PRUNE_MIN_ROWS = 262144        # below this the full contraction takes milliseconds
+PRUNE_MAX_DIM = 256
+PRUNE_CONTRAST = 0.4           # k-th neighbour distance / distance between random rows (knn_pruned.contrast)
+
+
+def prune_applicable(n_rows: int, dim: int, k: int) -> bool:
+    import os
+    return (n_rows >= PRUNE_MIN_ROWS and dim <= PRUNE_MAX_DIM and k + 1 <= 64
+            and os.environ.get("MMUMAP_KNN_PRUNE", "1") == "1")
 
 
 def _call(query, db, k, exclude_self, query_base, gid, same, min_splits, precision=0):
@@ -35,8 +44,10 @@ def _call(query, db, k, exclude_self, query_base, gid, same, min_splits, precisi
     return idx, dist, st, fallback
 
 
-def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, query_base: int = 0):
-    """Returns (idx int32 [Q,k] sorted by (dist, idx), dist float32 [Q,k])."""
+def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, query_base: int = 0, prune: bool | None = None):
+    """Returns (idx int32 [Q,k] sorted by (dist, idx), dist float32 [Q,k]).  prune: None = the cluster-pruned search
+    (knn_pruned.py) where it applies and pays, False = never, True = pruned or nothing (returns None when it does not
+    apply: the multi-GPU caller then runs its row-sharded full search instead of a replicated one)."""
     native.require_cuda()
     if k > native.KNN_TC_MAX_K:
         raise ValueError(f"tensor-core kNN supports k <= {native.KNN_TC_MAX_K}, got {k}")
@@ -49,7 +60,26 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
     # candidate pool depth: one 64-entry list certifies k <= 16 comfortably; deeper pools for larger k
     min_splits = 0 if k <= 16 else 2
     precision = 0
-    if q >= 65536 and n >= 65536 and (k > 16 or query.shape[1] <= 256):
+    pruned = None
+    if prune is not False and same and exclude_self and prune_applicable(q, query.shape[1], k):
+        # large, low-dimensional input: if its neighbourhoods are small against the typical distance between rows
+        # (clustered data), search cluster by cluster with exact ball bounds instead of the full contraction
+        from . import knn_pruned
+        ratio = knn_pruned.contrast(db, k)
+        if ratio < PRUNE_CONTRAST:
+            pruned = knn_pruned.knn_pruned(db, k)
+    if prune is True and pruned is None:
+        return None
+    if pruned is not None:
+        from . import knn_pruned
+        idx, dist, fb_rows = pruned
+        n_fb = n_first = int(fb_rows.numel())
+        fallback = fb_rows.to(torch.int32)
+        certified = q - n_fb
+        rescored = int(knn_pruned.last_stats.get("rescored_per_row", 0.0) * certified)
+        min_splits, precision = 0, 1
+        last_stats_extra = dict(knn_pruned.last_stats, contrast=ratio)
+    elif q >= 65536 and n >= 65536 and (k > 16 or query.shape[1] <= 256):
         # probe a strided sample of rows: when the data's neighbourhood gaps are small against the fp16
         # error bound (low dimension, large N, large norms), go straight to the deep pool for all rows
         step = q // 2048
@@ -58,9 +88,11 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
         _, _, pst, _ = _call(query.index_select(0, rows), db, k, exclude_self, 0, gid, False, min_splits)
         if pst[0] > 0.1 * rows.numel():
             precision = 1          # split operands shrink the error bound ~2000x: the shallow pool suffices again
-    idx, dist, st, fallback = _call(query, db, k, exclude_self, query_base, None, same, min_splits, precision)
-    n_fb = n_first = int(st[0])
-    rescored, certified = st[1], st[2]
+    if pruned is None:
+        idx, dist, st, fallback = _call(query, db, k, exclude_self, query_base, None, same, min_splits, precision)
+        n_fb = n_first = int(st[0])
+        rescored, certified = st[1], st[2]
+        last_stats_extra = {}
     if n_fb and not (precision == 1 and min_splits >= DEEP_SPLITS):
         # second level: only the uncertified rows, database in 8 splits (512 candidates per row), split operands
         rows = fallback[:n_fb].long()
@@ -79,5 +111,5 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
     last_stats.clear()
     last_stats.update(rows=q, first_pass_uncertified=n_first, fallback_rows=n_fb, certified_rows=int(certified),
                       rescored_per_row=(rescored / certified) if certified else 0.0, min_splits=min_splits,
-                      precision=precision)
+                      precision=precision, pruned=pruned is not None, **last_stats_extra)
     return idx, dist

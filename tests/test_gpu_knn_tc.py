@@ -190,3 +190,40 @@ def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind):
     finally:
         for key, val in defaults.items():
             native.set_option(key, val)
+
+
+@pytest.mark.parametrize("n,d,k,blobs", [(60000, 64, 30, 200), (40000, 128, 15, 50), (30011, 16, 10, 300)])
+def test_cluster_pruned_search_bit_exact(n, d, k, blobs):
+    """knn_pruned.knn_pruned (rows sorted by cluster, per-block tile ranges / lists, ball bounds, original indices
+    through db_gid) must equal the exhaustive kernel bit for bit on every row it reports as done, and must actually
+    prune on clustered data; the rows it hands back as uncertified are finished by knn_tc's deeper levels."""
+    from umap_b200 import graph as G
+    from umap_b200 import knn_pruned, knn_tc
+    g = torch.Generator(device="cuda").manual_seed(n + d)
+    centres = 5.0 * torch.randn((blobs, d), generator=g, device="cuda")
+    x = (centres[torch.arange(n, device="cuda") % blobs] + torch.randn((n, d), generator=g, device="cuda")).contiguous()
+    x[123] = x[77]                                            # an exact duplicate: a distance tie decided by ORIGINAL index
+    x[5000:5040] = x[5000]                                    # and a run of 40 identical rows
+    assert knn_pruned.contrast(x, k) < knn_tc.PRUNE_CONTRAST
+    res = knn_pruned.knn_pruned(x, k, n_centroids=512)
+    assert res is not None, knn_pruned.last_stats
+    idx, dist, fb = res
+    st = dict(knn_pruned.last_stats)
+    assert st["visited_tile_fraction"] < 0.35, st
+    si, sd = G.knn_exact_simt(x, x, k, True)
+    done = torch.ones(n, dtype=torch.bool, device="cuda")
+    done[fb] = False
+    assert int(fb.numel()) < 0.01 * n, st
+    assert torch.equal(idx[done], si[done]), f"{int((idx[done] != si[done]).any(dim=1).sum())} rows differ"
+    assert torch.equal(dist[done].view(torch.int32), sd[done].view(torch.int32))
+
+
+def test_pruned_search_declines_on_unclustered_data():
+    """Uniform noise has no cluster structure: the contrast heuristic says so, and a forced attempt finds that its tile
+    lists cover most of the database and returns None (the caller then runs the full contraction)."""
+    from umap_b200 import knn_pruned, knn_tc
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((40000, 64), generator=g, device="cuda").contiguous()
+    assert knn_pruned.contrast(x, 15) > knn_tc.PRUNE_CONTRAST
+    assert knn_pruned.knn_pruned(x, 15, n_centroids=256) is None
+    assert knn_pruned.last_stats["visited_tile_fraction"] > 0.5
