@@ -152,42 +152,48 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     u = (kth + eps + x2).clamp(min=0.0)
     valid_row = (torch.arange(n_qb * bm, device=dev).view(n_qb, bm) + q_lo) < q_hi
     u = torch.where(valid_row, u, torch.zeros_like(u))
-    r_k = u.amax(dim=1).sqrt() / scale                                                 # original units, per query block
-    # rho_block = largest |x - c_a0| over the block's rows
-    rho = torch.empty(n_qb, device=dev)
-    step = max(1, (1 << 28) // (bm * dim * 4))
-    for b0 in range(0, n_qb, step):
-        b1 = min(n_qb, b0 + step)
-        r0, r1 = b0 * bm, min(nq, b1 * bm)
-        blk = torch.zeros(((b1 - b0) * bm, dim), device=dev)
-        blk[: r1 - r0] = xq[r0:r1]
-        d = (blk.view(b1 - b0, bm, dim) - cent.index_select(0, a0[b0:b1])[:, None, :]).norm(dim=2)
-        vr = valid_row[b0:b1]
-        rho[b0:b1] = torch.where(vr, d, torch.zeros_like(d)).amax(dim=1)
+    # A 128-row query block of the sorted order usually straddles clusters (clusters are ~N/C rows, and neighbouring
+    # cluster ids are unrelated places), so the bound is taken per SEGMENT = the rows of one cluster inside one block:
+    # centre = the cluster's centroid, rho_seg = largest member distance |x - c_a| among the segment's rows (known exactly
+    # from the assignment), r_seg = largest k-th-neighbour bound among them.  A block searches the union of its segments' needs.
+    rows_local = torch.arange(nq, device=dev)
+    row_u = u.reshape(-1)[:nq]
+    row_rk = row_u.sqrt() / scale                                                      # original units, per row
+    row_a = assign[q_lo:q_hi]
+    row_rho = a_dist.index_select(0, perm[q_lo:q_hi])
+    seg_key = (rows_local // bm) * n_centroids + row_a
+    _, seg_of_row = torch.unique_consecutive(seg_key, return_inverse=True)
+    n_seg = int(seg_of_row[-1].item()) + 1 if nq else 0
+    seg_rk = torch.zeros(n_seg, device=dev).scatter_reduce(0, seg_of_row, row_rk, reduce="amax", include_self=True)
+    seg_rho = torch.zeros(n_seg, device=dev).scatter_reduce(0, seg_of_row, row_rho, reduce="amax", include_self=True)
+    seg_a = torch.zeros(n_seg, dtype=torch.int64, device=dev).scatter_(0, seg_of_row, row_a)
+    seg_qb = torch.zeros(n_seg, dtype=torch.int64, device=dev).scatter_(0, seg_of_row, rows_local // bm)
     cd = torch.cdist(cent, cent, compute_mode="donot_use_mm_for_euclid_dist")
     nonempty = counts > 0
     ts = (starts // bn).to(torch.int64)
     te = torch.where(nonempty, (ends - 1) // bn, ts - 1).to(torch.int64)               # inclusive; empty cluster: no tiles
-    qb_ids, tile_ids = [], []
+    keys = []
     chunk = max(1, (1 << 26) // n_centroids)
-    for b0 in range(0, n_qb, chunk):
-        b1 = min(n_qb, b0 + chunk)
-        lb = cd.index_select(0, a0[b0:b1]) - rho[b0:b1, None] - radius[None, :]
-        need = (lb * (1.0 - SAFETY) <= r_k[b0:b1, None] * (1.0 + SAFETY)) & nonempty[None, :]
-        qb, cl = need.nonzero(as_tuple=True)
-        if qb.numel() == 0:
+    for s0 in range(0, n_seg, chunk):
+        s1 = min(n_seg, s0 + chunk)
+        lb = cd.index_select(0, seg_a[s0:s1]) - seg_rho[s0:s1, None] - radius[None, :]
+        need = (lb * (1.0 - SAFETY) <= seg_rk[s0:s1, None] * (1.0 + SAFETY)) & nonempty[None, :]
+        sg, cl = need.nonzero(as_tuple=True)
+        if sg.numel() == 0:
             continue
         cnt = (te[cl] - ts[cl] + 1)
-        rep_qb = torch.repeat_interleave(qb + b0, cnt)
+        rep_qb = torch.repeat_interleave(seg_qb[s0:s1][sg], cnt)
         base = torch.repeat_interleave(ts[cl], cnt)
         offs = torch.arange(rep_qb.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
         tl = base + offs
-        # clusters are visited in ascending order: a tile shared by two neighbouring clusters appears twice in a row
-        keep = torch.ones_like(tl, dtype=torch.bool)
-        keep[1:] = (tl[1:] != tl[:-1]) | (rep_qb[1:] != rep_qb[:-1])
-        keep &= (tl < t_begin[rep_qb].long()) | (tl >= t_end[rep_qb].long())            # pass 1 already searched these
-        qb_ids.append(rep_qb[keep])
-        tile_ids.append(tl[keep])
+        keep = (tl < t_begin[rep_qb].long()) | (tl >= t_end[rep_qb].long())             # pass 1 already searched these
+        keys.append(torch.unique(rep_qb[keep] * n_tiles + tl[keep]))
+    qb_ids, tile_ids = [], []
+    if keys:
+        # a tile can be needed by several segments of a block and by neighbouring clusters: no tile twice per block
+        key = torch.unique(torch.cat(keys))
+        qb_ids.append(key // n_tiles)
+        tile_ids.append(key % n_tiles)
     if qb_ids:
         qb_all = torch.cat(qb_ids)
         tiles_all = torch.cat(tile_ids).to(torch.int32)
