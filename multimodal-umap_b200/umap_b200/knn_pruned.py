@@ -99,6 +99,16 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     a_idx = a_idx[:, 0].long()
     a_dist = a_dist[:, 0]
     perm = torch.argsort(a_idx, stable=True)
+    # Inside every full 256-row tile the sorted rows are dealt round-robin to the tile's four 64-column slices
+    # (row j of the tile goes to slot (j mod 4) * 64 + j div 4).  The candidates kernel keeps one 16-entry list per row
+    # and COLUMN SLICE (knn_tc.cu, TC_EPI_GROUPS): in cluster order a row's neighbours sit in a few adjacent columns,
+    # one slice would have to hold most of the top k and could not certify; dealt out, every slice sees a quarter.
+    full = (n // 256) * 256
+    if full:
+        j = torch.arange(256, device=dev)
+        slot_src = torch.empty(256, dtype=torch.int64, device=dev)
+        slot_src[(j % 4) * 64 + j // 4] = j                       # slot -> source row of the tile
+        perm[:full] = perm[:full].view(-1, 256).index_select(1, slot_src).reshape(-1)
     assign = a_idx.index_select(0, perm)
     counts = torch.bincount(a_idx, minlength=n_centroids)
     ends = torch.cumsum(counts, 0)
@@ -134,10 +144,11 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
 
     stage(1)
     # ---- 4: pass 1 over the home clusters' tiles (one contiguous range per query block)
-    first = torch.arange(n_qb, device=dev, dtype=torch.int64) * bm + q_lo
-    last = torch.clamp(first + bm, max=q_hi) - 1
-    a0 = assign.index_select(0, first)
-    a1 = assign.index_select(0, last)
+    blk_assign = torch.full((n_qb * bm,), -1, dtype=torch.int64, device=dev)
+    blk_assign[:nq] = assign[q_lo:q_hi]
+    a1 = blk_assign.view(n_qb, bm).amax(dim=1)                                          # largest / smallest cluster id in the block
+    blk_assign[nq:] = n_centroids
+    a0 = blk_assign.view(n_qb, bm).amin(dim=1)
     t_begin = (starts.index_select(0, a0) // bn).to(torch.int32)
     t_end = ((ends.index_select(0, a1) + bn - 1) // bn).to(torch.int32)
     stage(2, tb=t_begin, te=t_end)

@@ -13,4 +13,6 @@ for _ in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); knn_tc.knn_tc(x, x, k, True); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"{n}x{d} k={k}: {ms:.1f} ms  {2.0*n*n*d/ms/1e9:.1f} TFLOP/s  {knn_tc.last_stats}", flush=True)
+    print(f"{n}x{d} k={k}: {ms:.1f} ms  {2.0*n*n*d/ms/1e9:.1f} TFLOP/s (algorithmic 2QND)  {knn_tc.last_stats}", flush=True)
+from umap_b200 import knn_pruned
+print("contrast", knn_pruned.contrast(x, k), "pruned stats", knn_pruned.last_stats, flush=True)
