@@ -39,17 +39,27 @@ SAFETY = 1e-3
 ONE_SPLIT = -1                 # min_splits value that pins the search to a single database split (one 64-entry list per row)
 
 
+def _spread_rows(n: int, count: int, device) -> torch.Tensor:
+    """`count` distinct row numbers spread over [0, n) by multiplicative hashing: deterministic (every rank picks the same
+    rows, no RNG state consumed) and -- unlike a fixed stride -- not in resonance with periodic row orders (synthetic data
+    laid out cluster by cluster modulo the cluster count: a stride of 15 over 1000 clusters only ever sees 200 of them)."""
+    count = min(count, n)
+    i = torch.arange(count, device=device, dtype=torch.int64)
+    rows = (i * 2654435761 + 12345) % n
+    return torch.unique(rows) if count < n else torch.arange(n, device=device, dtype=torch.int64)
+
+
 def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
     """median k-th neighbour distance of a strided row sample / median distance between random rows: small when the
     data is clustered at the scale of its neighbourhoods, i.e. when ball bounds can prune."""
     from .knn_tc import _call
     n = x.shape[0]
-    rows = torch.arange(0, n, max(1, n // sample), device=x.device, dtype=torch.int64)[:sample]
+    rows = _spread_rows(n, sample, x.device)
     _, dist, st, fb = _call(x.index_select(0, rows), x, k, True, 0, rows.to(torch.int32), False, 0, 1)
     ok = torch.ones(rows.numel(), dtype=torch.bool, device=x.device)
     ok[fb[: int(st[0])].long()] = False                     # uncertified rows are not written by the call
     ok &= torch.isfinite(dist[:, k - 1]) & (dist[:, k - 1] > 0)
-    if int(ok.sum()) < sample // 2:
+    if int(ok.sum()) < rows.numel() // 2:
         return 1.0
     dk = dist[ok, k - 1].median()
     other = x.index_select(0, (rows * 7919 + 13) % n)
@@ -60,7 +70,7 @@ def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
 def farthest_point_centroids(x: torch.Tensor, n_centroids: int, sub_rows: int = 65536) -> torch.Tensor:
     """Greedy k-centre on a strided subsample: deterministic (no RNG: every rank gets the same centroids)."""
     n = x.shape[0]
-    sub = x[:: max(1, n // sub_rows)][:sub_rows].contiguous()
+    sub = x if n <= sub_rows else x.index_select(0, _spread_rows(n, sub_rows, x.device))
     d2 = torch.full((sub.shape[0],), float("inf"), device=x.device)
     cent = torch.empty((n_centroids, x.shape[1]), dtype=torch.float32, device=x.device)
     i = torch.zeros((), dtype=torch.int64, device=x.device)

@@ -192,8 +192,8 @@ def test_cta_pairs_windowed_and_single_cta_forms_agree(n, d, kind):
             native.set_option(key, val)
 
 
-@pytest.mark.parametrize("n,d,k,blobs", [(60000, 64, 30, 200), (40000, 128, 15, 50), (30011, 16, 10, 300)])
-def test_cluster_pruned_search_bit_exact(n, d, k, blobs):
+@pytest.mark.parametrize("n,d,k,blobs,cents", [(60000, 64, 30, 200, 256), (40000, 128, 15, 50, 64), (30011, 16, 10, 300, 320)])
+def test_cluster_pruned_search_bit_exact(n, d, k, blobs, cents):
     """knn_pruned.knn_pruned (rows sorted by cluster, per-block tile ranges / lists, ball bounds, original indices
     through db_gid) must equal the exhaustive kernel bit for bit on every row it reports as done, and must actually
     prune on clustered data; the rows it hands back as uncertified are finished by knn_tc's deeper levels."""
@@ -205,7 +205,7 @@ def test_cluster_pruned_search_bit_exact(n, d, k, blobs):
     x[123] = x[77]                                            # an exact duplicate: a distance tie decided by ORIGINAL index
     x[5000:5040] = x[5000]                                    # and a run of 40 identical rows
     assert knn_pruned.contrast(x, k) < knn_tc.PRUNE_CONTRAST
-    res = knn_pruned.knn_pruned(x, k, n_centroids=512)
+    res = knn_pruned.knn_pruned(x, k, n_centroids=cents)
     assert res is not None, knn_pruned.last_stats
     idx, dist, fb = res
     st = dict(knn_pruned.last_stats)
