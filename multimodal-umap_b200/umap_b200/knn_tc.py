@@ -78,7 +78,7 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
         certified = q - n_fb
         rescored = int(knn_pruned.last_stats.get("rescored_per_row", 0.0) * certified)
         min_splits, precision = 0, 1
-        last_stats_extra = dict(knn_pruned.last_stats, contrast=ratio)
+        last_stats_extra = {"pruning": dict(knn_pruned.last_stats, contrast=ratio)}
     elif q >= 65536 and n >= 65536 and (k > 16 or query.shape[1] <= 256):
         # probe a strided sample of rows: when the data's neighbourhood gaps are small against the fp16
         # error bound (low dimension, large N, large norms), go straight to the deep pool for all rows
