@@ -610,9 +610,15 @@ def run_b200(args, workload, data):
     forces_gbs = forces["bytes"] / (forces["ms"] * 1e-3) / 1e9 if forces["ms"] > 0 else 0.0
     kf = facts.get("knn_candidates", {})
     ff = facts.get("edge_forces", {})
+    from umap_b200 import knn_tc as _kt
+    pruning = _kt.last_stats.get("pruning") if _kt.last_stats.get("pruned") else None
     roof_knn = {"kernel": f"knn_tc: tc_prep + {knn_kernel or 'knn_tc_candidates_kernel'} [tcgen05] + knn_tc_rescore_kernel",
                 "bound": "tensor", "achieved": knn_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": knn_tflops / tensor_peak, "traffic": kf.get("dram_bytes_per_launch"), "peak_source": peak_src,
+                # cluster-pruned search (knn_pruned.py): `achieved` is the ALGORITHMIC 2QND of the exhaustive search per second;
+                # the tensor cores evaluate only visited_tile_fraction of it (x3 for the split-fp16 operands), so frac > 1
+                # measures the pruning, not the tensor pipe
+                "pruned_search": pruning,
                 "share_of_step": knn["ms"] / total_ms if total_ms else None,
                 "ms_per_launch": knn["ms"] / max(knn["calls"], 1), "ncu": kf or None}
     # the force kernel: algorithmic bytes per launch / measured launch time, against the HBM copy peak as
