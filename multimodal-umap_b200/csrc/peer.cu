@@ -226,6 +226,107 @@ epoch_tail_peer_kernel(PeerPtrs params, PeerPtrs grads, PeerPtrs flags, const fl
     }
 }
 
+// ------------------------------------------------------------------ push form of the epoch tail (small tables)
+// The pull form above is a chain of NVLink round trips (flag -> remote load / in-switch reduce -> store -> flag:
+// measured 67 us per epoch on 12 MB tables at 2 AND at 8 GPUs, i.e. latency, not volume).  Here nothing is ever loaded
+// from a peer -- remote STORES are posted, a rank only waits for flags:
+//   A. every rank PUSHES its partial gradient to the owners' inboxes (shard s of my buffer -> slot `rank` of rank s's
+//      inbox) and zeroes its own buffer as it goes (local); the last block to finish fences and raises flag slot 0;
+//   B. every rank waits for the W flags, sums the W slots of its inbox (LOCAL loads, fixed order), applies Adam once
+//      and pushes the new parameters into all W replicas; the last block fences and raises flag slot 1; block 0 waits
+//      for the W slot-1 flags and advances the optimiser state.
+// Two one-way hops instead of five.  Per rank and epoch 2 x (W-1)/W of the buffer leaves over NVLink (the pull form
+// with multimem moves half of that), which is why this form is used for small tables only (where latency is the cost).
+// The grid is one block per SM: blocks spin on peers' flags, so all of them have to become resident.
+template <int WT>
+__global__ void __launch_bounds__(256)
+epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *__restrict__ grad, float *__restrict__ m,
+                       float *__restrict__ v, int64_t n4, int64_t slot4, int world_rt, int rank, double lr, double beta1d,
+                       double beta2d, float beta2, float omb1, float omb2, float eps, OptState *__restrict__ st,
+                       unsigned int *__restrict__ done_counter, uint32_t *__restrict__ seq_word) {
+    const int world = WT ? WT : world_rt;
+    const uint32_t seq = *seq_word + 1u;
+    __shared__ float s_step[2];
+    __shared__ unsigned int s_last;
+    if (threadIdx.x == 0) {
+        const uint32_t step = st->step + 1;
+        s_step[0] = (float)(lr / (1.0 - pow(beta1d, (double)step)));
+        s_step[1] = (float)sqrt(1.0 - pow(beta2d, (double)step));
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- A: push my partial gradient to the owners, clear it
+    float4 *g4 = reinterpret_cast<float4 *>(grad);
+    for (int64_t i = tid; i < n4; i += stride) {
+        // owner s of element i: the largest s with n4*s/world <= i
+        int s = (int)(((i + 1) * world - 1) / n4);
+        if (s >= world) s = world - 1;
+        while (s > 0 && n4 * s / world > i) --s;
+        while (s + 1 < world && n4 * (s + 1) / world <= i) ++s;
+        const int64_t lo_s = n4 * s / world;
+        const float4 gv = g4[i];
+        st_peer(reinterpret_cast<float4 *>(inbox.p[s]) + (int64_t)rank * slot4 + (i - lo_s), gv);
+        g4[i] = zero;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence_system();
+        flags_arrive(flags, world, rank, 0, seq);
+    }
+    // ---- B: my shard is complete in my inbox once every rank has raised slot 0
+    if (threadIdx.x < 32) flags_wait(flags, world, rank, 0, seq);
+    __syncthreads();
+    const float neg_step = -s_step[0], bc2_sqrt = s_step[1];
+    auto upd = [&](float &pp, float gg, float &mm, float &vv) {       // adam_kernel's arithmetic (layout_sgd.cu)
+        mm = __fadd_rn(mm, __fmul_rn(omb1, __fsub_rn(gg, mm)));
+        vv = __fadd_rn(__fmul_rn(vv, beta2), __fmul_rn(__fmul_rn(omb2, gg), gg));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
+        pp = __fadd_rn(pp, __fdiv_rn(__fmul_rn(neg_step, mm), denom));
+    };
+    const int64_t lo4 = n4 * rank / world, hi4 = n4 * (rank + 1) / world;
+    const float4 *in4 = reinterpret_cast<const float4 *>(inbox.p[rank]);
+    for (int64_t i = lo4 + tid; i < hi4; i += stride) {
+        float4 gg = ld_peer(in4 + (i - lo4));                                   // slot 0; L1 may hold last epoch's line
+        for (int w = 1; w < world; ++w) {                                       // fixed order: a deterministic sum
+            const float4 u = ld_peer(in4 + (int64_t)w * slot4 + (i - lo4));
+            gg.x = __fadd_rn(gg.x, u.x); gg.y = __fadd_rn(gg.y, u.y); gg.z = __fadd_rn(gg.z, u.z); gg.w = __fadd_rn(gg.w, u.w);
+        }
+        float4 pp = reinterpret_cast<const float4 *>(params.p[rank])[i];
+        float4 mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
+        upd(pp.x, gg.x, mm.x, vv.x);
+        upd(pp.y, gg.y, mm.y, vv.y);
+        upd(pp.z, gg.z, mm.z, vv.z);
+        upd(pp.w, gg.w, mm.w, vv.w);
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+        for (int w = 0; w < world; ++w) st_peer(reinterpret_cast<float4 *>(params.p[w]) + i, pp);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == 2u * gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence_system();
+        flags_arrive(flags, world, rank, 1, seq);
+        if (threadIdx.x == 0) *done_counter = 0u;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 32) flags_wait(flags, world, rank, 1, seq);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st->step = st->step + 1;
+            st->epoch = st->epoch + 1;
+            st->step_size = s_step[0];
+            st->bc2_sqrt = s_step[1];
+            *seq_word = seq;
+        }
+    }
+}
+
 static int fill_ptrs(PeerPtrs &dst, const uint64_t *src, int world) {
     for (int w = 0; w < MMU_PEER_MAX; ++w) dst.p[w] = w < world ? src[w] : 0;
     for (int w = 0; w < world; ++w)
@@ -314,6 +415,41 @@ extern "C" int mmu_epoch_tail_peer(const uint64_t *peer_params, const uint64_t *
     else MMU_TAIL(false, 0);
 #undef MMU_TAIL
     note_kernel(SITE_EPOCH_TAIL, "epoch_tail_peer_kernel<%s,W=%d>", mc_params ? "multimem" : "peer-loads", world);
+    MMU_LAUNCH_CHECK();
+    return MMU_OK;
+}
+
+extern "C" int mmu_epoch_tail_push(const uint64_t *peer_params, const uint64_t *peer_inbox, const uint64_t *peer_flags,
+                                   float *grad, float *m, float *v, int64_t n, int64_t inbox_slot_floats, int world, int rank,
+                                   double lr, double beta1, double beta2, double eps, uint32_t *state, uint32_t *done_counter,
+                                   mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(peer_params && peer_inbox && peer_flags && grad && m && v && state && done_counter,
+                  "mmu_epoch_tail_push: null pointer");
+    MMU_CHECK_ARG(world >= 1 && world <= MMU_PEER_MAX && rank >= 0 && rank < world, "mmu_epoch_tail_push: bad world/rank");
+    MMU_CHECK_ARG(n >= 0 && (n & 3) == 0 && (inbox_slot_floats & 3) == 0, "mmu_epoch_tail_push: sizes must be multiples of 4");
+    const int64_t n4 = n >> 2, slot4 = inbox_slot_floats >> 2;
+    MMU_CHECK_ARG(slot4 >= (n4 + world - 1) / world, "mmu_epoch_tail_push: inbox slot smaller than a shard");
+    MMU_CHECK_ARG(((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+                  "mmu_epoch_tail_push: grad / m / v must be 16-byte aligned");
+    PeerPtrs pp, ib, ff;
+    MMU_CHECK_ARG(fill_ptrs(pp, peer_params, world) == 0 && fill_ptrs(ib, peer_inbox, world) == 0 &&
+                  fill_ptrs(ff, peer_flags, world) == 0, "mmu_epoch_tail_push: null or unaligned peer pointer");
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    const unsigned blocks = (unsigned)sms;                 // every block spins on peers' flags: all must become resident
+    OptState *os = reinterpret_cast<OptState *>(state);
+    cudaStream_t st = as_stream(stream);
+#define MMU_PUSH(WTV)                                                                                                       \
+    epoch_tail_push_kernel<WTV><<<blocks, 256, 0, st>>>(pp, ib, ff, grad, m, v, n4, slot4, world, rank, lr, beta1, beta2,   \
+                                                        (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, \
+                                                        os, done_counter, done_counter + 1)
+    if (world == 2) MMU_PUSH(2);
+    else if (world == 4) MMU_PUSH(4);
+    else if (world == 8) MMU_PUSH(8);
+    else MMU_PUSH(0);
+#undef MMU_PUSH
+    note_kernel(SITE_EPOCH_TAIL, "epoch_tail_push_kernel<W=%d>", world);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

@@ -100,14 +100,35 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     dev = x.device
     n, dim = x.shape
     world, rank = D.world(), D.rank()
+    debug = os.environ.get("MMUMAP_KNN_DEBUG") == "1"
+    marks = []
+
+    def mark(label):
+        if debug:
+            import time
+            torch.cuda.synchronize()
+            marks.append((label, time.perf_counter()))
+
+    mark("start")
     if n_centroids is None:
         n_centroids = int(min(8192, max(256, 2 ** round(math.log2(1.3 * math.sqrt(n))))))
     # ---- 1-3: centroids, assignment, cluster order
     cent = farthest_point_centroids(x, n_centroids)
+    mark("centroids (farthest-point sampling)")
     from .knn_tc import knn_tc
-    a_idx, a_dist = knn_tc(x, cent, 1, False)               # nearest centroid and the canonical fp32 distance to it
+    if world > 1:
+        # every rank assigns a block of rows; the blocks are all-gathered
+        lo, hi = D.row_block(n, rank, world)
+        a_i, a_d = knn_tc(x[lo:hi].contiguous(), cent, 1, False) if hi > lo else (
+            torch.zeros((0, 1), dtype=torch.int32, device=dev), torch.zeros((0, 1), dtype=torch.float32, device=dev))
+        per = D.block_size(n, world)
+        a_idx = D.all_gather_rows(a_i, n, per)
+        a_dist = D.all_gather_rows(a_d, n, per)
+    else:
+        a_idx, a_dist = knn_tc(x, cent, 1, False)           # nearest centroid and the canonical fp32 distance to it
     a_idx = a_idx[:, 0].long()
     a_dist = a_dist[:, 0]
+    mark("assignment (kNN k=1 against the centroids)")
     perm = torch.argsort(a_idx, stable=True)
     # Inside every full 256-row tile the sorted rows are dealt round-robin to the tile's four 64-column slices
     # (row j of the tile goes to slot (j mod 4) * 64 + j div 4).  The candidates kernel keeps one 16-entry list per row
@@ -152,7 +173,9 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
                               ptr(idx), ptr(dist), ptr(stats), ptr(fallback), mask, ptr(tb), ptr(te), ptr(tp), ptr(tl), resume,
                               ptr(perm32), st), "mmu_knn_tc_ex")
 
+    mark("cluster order, permuted copy")
     stage(1)
+    mark("prep (fp16 split operands)")
     # ---- 4: pass 1 over the home clusters' tiles (one contiguous range per query block)
     blk_assign = torch.full((n_qb * bm,), -1, dtype=torch.int64, device=dev)
     blk_assign[:nq] = assign[q_lo:q_hi]
@@ -162,6 +185,7 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     t_begin = (starts.index_select(0, a0) // bn).to(torch.int32)
     t_end = ((ends.index_select(0, a1) + bn - 1) // bn).to(torch.int32)
     stage(2, tb=t_begin, te=t_end)
+    mark("pass 1 (home clusters)")
     # ---- 5: bound.  U (scaled, squared) >= true k-th neighbour distance of every row of the block
     prm, xnorm, cscore = _views(ws, words, nq)
     scale = prm[0]
@@ -229,11 +253,13 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     last_stats.clear()
     last_stats.update(rows=n, centroids=n_centroids, query_blocks=n_qb, tiles=n_tiles, visited_tile_fraction=fraction,
                       pass1_tiles=int((t_end - t_begin).sum().item()), pass2_tiles=int(tiles_all.numel()))
+    mark("bounds and tile lists")
     if fraction > max_fraction:
         return None
     # ---- 6: pass 2
     if tiles_all.numel():
         stage(2, tp=tile_ptr, tl=tiles_all.contiguous(), resume=1)
+    mark("pass 2 (listed tiles)")
     # ---- 7: certification + canonical fp32 rescoring, original indices
     stage(4)
     st_host = stats.tolist()
@@ -255,4 +281,7 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     out_idx.index_copy_(0, perm, idx)
     out_dist.index_copy_(0, perm, dist)
     last_stats.update(uncertified_rows=int(fb_sorted.numel()), rescored_per_row=st_host[1] / max(st_host[2], 1))
+    mark("certify + rescore, gather, un-permute")
+    if debug and rank == 0:
+        print("  knn_pruned " + ", ".join(f"{b[0]} {(b[1] - a[1]) * 1e3:.1f} ms" for a, b in zip(marks, marks[1:])), flush=True)
     return out_idx, out_dist, perm.index_select(0, fb_sorted)

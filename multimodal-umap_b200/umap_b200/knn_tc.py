@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import torch
 
+from . import dist as D
 from . import native
 from .native import check, lib, ptr, stream
 
@@ -93,6 +94,12 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
         n_fb = n_first = int(st[0])
         rescored, certified = st[1], st[2]
         last_stats_extra = {}
+    shard_fb = None
+    if pruned is not None and n_fb and D.world() > 1:
+        # multi-GPU: the rows the pruned pass left open are known to every rank; each finishes every W-th of them
+        shard_fb = fallback[:n_fb].long()
+        fallback = shard_fb[D.rank()::D.world()].to(torch.int32).contiguous()
+        n_fb = int(fallback.numel())
     if n_fb and not (precision == 1 and min_splits >= DEEP_SPLITS):
         # second level: only the uncertified rows, database in 8 splits (512 candidates per row), split operands
         rows = fallback[:n_fb].long()
@@ -108,6 +115,30 @@ def knn_tc(query: torch.Tensor, db: torch.Tensor, k: int, exclude_self: bool, qu
         fallback = fallback[:n_fb].contiguous()
         check(lib().mmu_knn_exact_f32(ptr(query), n_fb, ptr(fallback), ptr(db), n, query.shape[1], k, int(exclude_self),
                                       query_base, 0, 0, ptr(idx), ptr(dist), stream()), "mmu_knn_exact_f32(fallback)")
+    if shard_fb is not None:
+        # exchange the finished rows: pad every rank's share to the same length and all-gather
+        import torch.distributed as tdist
+        w = D.world()
+        per = -(-int(shard_fb.numel()) // w)
+        mine = shard_fb[D.rank()::w]
+        pad_rows = torch.full((per,), -1, dtype=torch.int64, device=idx.device)
+        pad_rows[: mine.numel()] = mine
+        pad_i = torch.zeros((per, k), dtype=torch.int32, device=idx.device)
+        pad_d = torch.zeros((per, k), dtype=torch.float32, device=idx.device)
+        pad_i[: mine.numel()] = idx.index_select(0, mine)
+        pad_d[: mine.numel()] = dist.index_select(0, mine)
+        all_rows = torch.empty(w * per, dtype=torch.int64, device=idx.device)
+        all_i = torch.empty((w * per, k), dtype=torch.int32, device=idx.device)
+        all_d = torch.empty((w * per, k), dtype=torch.float32, device=idx.device)
+        tdist.all_gather_into_tensor(all_rows, pad_rows)
+        tdist.all_gather_into_tensor(all_i, pad_i)
+        tdist.all_gather_into_tensor(all_d, pad_d)
+        ok = all_rows >= 0
+        idx.index_copy_(0, all_rows[ok], all_i[ok])
+        dist.index_copy_(0, all_rows[ok], all_d[ok])
+        t = torch.tensor([n_fb], dtype=torch.int64, device=idx.device)
+        D.all_reduce_sum(t)
+        n_fb = int(t.item())
     last_stats.clear()
     last_stats.update(rows=q, first_pass_uncertified=n_first, fallback_rows=n_fb, certified_rows=int(certified),
                       rescored_per_row=(rescored / certified) if certified else 0.0, min_splits=min_splits,

@@ -26,6 +26,7 @@ BETA1, BETA2, EPS = 0.9, 0.999, 1e-8          # torch.optim.Adam defaults (model
 INFONCE_NEG = 9                               # n_neg + 1 draws per anchor (model.py:364,383)
 INFONCE_CHUNK = 1000                          # model.py:369
 INFONCE_TAU = 0.5                             # model.py:364
+PUSH_TAIL_MAX_BYTES = 32 << 20                # multi-GPU: tables up to this size use the push form of the epoch tail
 AUTO_WINDOW_MB = 80                           # p + g bytes of the tail rows of one force-kernel window (see _window_rows)
 
 
@@ -215,7 +216,9 @@ class LayoutOptimizer:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 n_flags = 2 * native.PEER_MAX                          # uint32 flags, kept in the tail of the buffer
-                sym = symm_mem.empty(2 * cap + n_flags, dtype=torch.float32, device=dev)
+                # [parameters | partial gradients | inbox (push exchange: W slots of ceil(cap / W) floats) | flags]
+                inbox_floats = cap + 64 * native.PEER_MAX
+                sym = symm_mem.empty(2 * cap + inbox_floats + n_flags, dtype=torch.float32, device=dev)
                 hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
                 sym.zero_()
             except Exception as exc:                                   # noqa: BLE001 - any failure means "not available"
@@ -244,7 +247,8 @@ class LayoutOptimizer:
                 mc = 0
             pr = {"sym": sym, "hdl": hdl, "seq": 0, "cap": cap,
                   "params": arr(*bases), "grads": arr(*[b + 4 * cap for b in bases]),
-                  "flags": arr(*[b + 8 * cap for b in bases]),
+                  "inbox": arr(*[b + 8 * cap for b in bases]),
+                  "flags": arr(*[b + 4 * (2 * cap + inbox_floats) for b in bases]),
                   "mc_params": mc, "mc_grads": (mc + 4 * cap) if mc else 0,
                   "done": torch.zeros(2, dtype=torch.int32, device=dev)}
             _PEER_CACHE["buf"] = pr
@@ -372,7 +376,24 @@ class LayoutOptimizer:
             # -> [all parameters delivered] -> clear my gradient buffer
             pr, w, r = self.peer, D.world(), D.rank()
             pr["seq"] += 1
-            if os.environ.get("MMUMAP_PEER_TAIL", "fused") == "fused":
+            tail = os.environ.get("MMUMAP_PEER_TAIL", "auto")
+            if tail == "auto":
+                # small tables: NVLink latency is the cost -> push form (two one-way hops); large tables: the pull form,
+                # whose in-switch reduction (multimem) moves half the bytes
+                tail = "push" if self.total * 4 <= PUSH_TAIL_MAX_BYTES else "fused"
+            if tail == "push":
+                slot = (-(-(self.total // 4) // w) + 1) * 4
+                with profiler.stage("epoch_tail", level=2):
+                    check(lib().mmu_epoch_tail_push(pr["params"], pr["inbox"], pr["flags"], ptr(g), ptr(m), ptr(v), self.total,
+                                                    slot, w, r, self.lr, BETA1, BETA2, EPS, ptr(self.state), ptr(pr["done"]),
+                                                    stream()), "mmu_epoch_tail_push")
+                self.done += 1
+                if self.loss is not None:
+                    D.all_reduce_sum(self.loss)
+                    self.losses.append(float(self.loss.item()))
+                    self.loss.zero_()
+                return
+            if tail == "fused":
                 # ONE launch: barrier + shard reduce + Adam + replica store + gradient clear + barrier + state advance
                 # (barrier sequence number on the device, pr["done"][1]: no per-epoch argument -> graph replayable;
                 #  pr["seq"] mirrors it on the host for the legacy barrier calls)
@@ -568,7 +589,7 @@ class LayoutOptimizer:
                      and (D.world() == 1 or (self.peer is None and os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1")))
         peer_graph = (self.peer is not None and self.sample_stream == "device" and self.loss is None and epochs >= 12
                       and self.mode in ("fit", "transform") and not profiler.enabled(2)
-                      and os.environ.get("MMUMAP_PEER_TAIL", "fused") == "fused"
+                      and os.environ.get("MMUMAP_PEER_TAIL", "auto") in ("auto", "fused", "push")
                       and os.environ.get("MMUMAP_EPOCH_GRAPH", "1") == "1")
         if peer_graph:
             self._run_graphed(epochs)

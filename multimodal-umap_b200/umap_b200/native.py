@@ -75,6 +75,8 @@ _SIGNATURES = {
                                    c_double, c_void_p, c_void_p]),
     "mmu_epoch_tail_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int64, c_int, c_int,
                                     c_uint32, c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "mmu_epoch_tail_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                    c_double, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "mmu_opt_state_init": (c_int, [c_void_p, c_void_p]),
     "mmu_opt_state_advance": (c_int, [c_void_p, c_double, c_double, c_double, c_void_p]),
     "mmu_edge_sample_range": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_void_p,

@@ -22,8 +22,7 @@ def tiny_graph(n):
 rows = [158915, 31783]
 embeds = [torch.randn((n, 16), device="cuda") * 0.01 for n in rows]
 graphs = [tiny_graph(n) for n in rows]
-for label, env, per_sm in (("fused multimem 1/SM", {}, 1), ("fused multimem 2/SM", {}, 2), ("fused multimem 4/SM", {}, 4), ("fused multimem 8/SM", {}, 8),
-                           ("fused peer loads 1/SM", {"MMUMAP_PEER_MULTIMEM": "0"}, 1), ("fused peer loads 4/SM", {"MMUMAP_PEER_MULTIMEM": "0"}, 4),
+for label, env, per_sm in (("push", {"MMUMAP_PEER_TAIL": "push"}, 1), ("fused multimem 1/SM", {"MMUMAP_PEER_TAIL": "fused"}, 1), ("fused peer loads 1/SM", {"MMUMAP_PEER_TAIL": "fused", "MMUMAP_PEER_MULTIMEM": "0"}, 1),
                            ("legacy 5 launches", {"MMUMAP_PEER_TAIL": "legacy"}, 1)):
     os.environ.pop("MMUMAP_PEER_TAIL", None)
     os.environ.update(env)

@@ -25,7 +25,7 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("tail", ["fused", "legacy"])
+@pytest.mark.parametrize("tail", ["push", "fused", "legacy"])
 def test_two_gpu_parity(tail):
     env = dict(os.environ, MMUMAP_PEER_TAIL=tail)
     run = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
