@@ -100,7 +100,7 @@ int mmu_knn_exact_f32(const float *query, int64_t n_query, const int32_t *query_
  * query_is_db != 0 (fit mode): query and db are the same array and share one fp16 copy.
  * out_idx holds db row numbers; exclude_self drops the pair j == query_index_base + q, or
  * j == query_gid[q] when query_gid (nullable, [n_query]) is given (gathered query rows).
- * min_splits (0..8, 0 = automatic, -1 = exactly one): the database range is searched in at least that many splits,
+ * min_splits (0..8, 0 = automatic; -S = exactly S): the database range is searched in at least that many splits,
  * each keeping its own 64 candidates per row -- a deeper candidate pool for rows whose
  * neighbourhood gaps are too small for one list to be certified (the host retries the rows of
  * fallback_rows with min_splits = 8 and precision = 1 before resorting to the exhaustive kernel).
@@ -132,7 +132,8 @@ int mmu_knn_tc(const float *query, int64_t n_query, const float *db, int64_t n_d
  * This is the exact pruned search of umap_b200/knn_pruned.py: rows sorted by cluster, pass 1 over the home clusters'
  * tiles, ball bounds |c_a - c_b| - r_block - R_b against the pass-1 k-th distance select the tiles of pass 2, and the
  * usual certification + canonical fp32 rescoring finishes; a row is exact because every tile NOT visited is farther
- * than its k-th neighbour by the triangle inequality.  Needs a single database split (min_splits = 0 on large inputs).
+ * than its k-th neighbour by the triangle inequality.  Needs a pinned split count (min_splits = -S): the S splits of a query
+ * block take its tiles in turn, each with its own candidate lists.
  * mmu_knn_tc_layout: byte offsets inside the workspace {prm (scale at float 0, max |Y|^2 bits at word 1), |X|^2, |Y|^2,
  * cand_idx, cand_score, tau} and {n_qblocks, n_splits, n_tiles, candidates per split, query-block rows, tile rows} in
  * out_words[12]; the error-bound constants {c_rel, c_norm, c_abs, gamma} of the certification in out_consts[4]. */
@@ -144,6 +145,14 @@ int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *db, int64_t 
                   const int32_t *tile_list, int resume, const int32_t *db_gid, mmu_stream_t stream);
 int mmu_knn_tc_layout(int64_t n_query, int64_t n_db, int dim, int query_is_db, int min_splits, int precision,
                       int64_t *out_words, float *out_consts);
+
+/* Farthest-point (greedy k-centre) sampling of n_centroids rows of `sub` [n_sub x dim], for the pruned search: round c
+ * picks the row farthest from the rows picked so far (round 0: row 0; ties: the smaller row number).  One persistent kernel,
+ * one CTA per SM with a grid-wide barrier per round.  out_centroids [n_centroids x dim], out_rows [n_centroids] (row
+ * numbers in `sub`).  workspace: mmu_fps_workspace_bytes(n_sub), 16-byte aligned. */
+size_t mmu_fps_workspace_bytes(int64_t n_sub);
+int mmu_fps_centroids(const float *sub, int64_t n_sub, int dim, int n_centroids, void *workspace, size_t workspace_bytes,
+                      float *out_centroids, int32_t *out_rows, mmu_stream_t stream);
 
 /* K3: merge two sorted per-row lists (e.g. from two db shards) into one sorted top-k. */
 int mmu_knn_merge(const int32_t *idx_a, const float *dist_a, const int32_t *idx_b,
@@ -224,6 +233,11 @@ int mmu_block_ctl_words(void);
 int mmu_block_ctl_init(float *ctl, mmu_stream_t stream);
 int mmu_block_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n, const float *x, int b,
                    const float *ctl, int coef_slot, const float *z, float *y, mmu_stream_t stream);
+/* rows [row_lo, row_hi) of the same product only (x, z, y are still whole n x B blocks): a rank's share when the operator
+ * applications of a large solve are sharded over GPUs and the row blocks of y are all-gathered afterwards. */
+int mmu_block_spmm_rows(const int64_t *rowptr, const int32_t *col, const float *val, int64_t row_lo, int64_t row_hi,
+                        const float *x, int b, const float *ctl, int coef_slot, const float *z, float *y,
+                        mmu_stream_t stream);
 size_t mmu_block_gram_workspace_bytes(int b);
 int mmu_block_gram(const float *x, const float *y, int64_t n, int b, int mode, void *workspace, float *g, float *dinv,
                    const float *ctl, mmu_stream_t stream);

@@ -43,13 +43,14 @@ __device__ __forceinline__ bool bc_done(const float *ctl) { return ctl && reinte
 template <int B>
 __global__ void __launch_bounds__(256)
 spmm_block_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const float *__restrict__ val,
-                  int64_t n, const float *__restrict__ x, const float *__restrict__ coef, const float *__restrict__ z,
-                  float *__restrict__ y, const float *__restrict__ ctl) {
+                  int64_t row_lo, int64_t n, const float *__restrict__ x, const float *__restrict__ coef,
+                  const float *__restrict__ z, float *__restrict__ y, const float *__restrict__ ctl) {
+    // rows [row_lo, n) of the operator (a rank's row block when the SpMM is sharded over GPUs; x is always the full block)
     if (bc_done(ctl)) return;
     constexpr int LPR = B / 4, RPW = 32 / LPR;
     const float alpha = coef[0], beta = coef[1], gamma = coef[2];
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-    const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + grp;
+    const int64_t r = row_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + grp;
     const bool live = r < n;
     const int64_t e0 = live ? rowptr[r] : 0, e1 = live ? rowptr[r + 1] : 0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -339,22 +340,30 @@ extern "C" int mmu_block_ctl_init(float *ctl, mmu_stream_t stream) {
 
 extern "C" int mmu_block_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n, const float *x, int b,
                               const float *ctl, int coef_slot, const float *z, float *y, mmu_stream_t stream) {
+    return mmu_block_spmm_rows(rowptr, col, val, 0, n, x, b, ctl, coef_slot, z, y, stream);
+}
+
+extern "C" int mmu_block_spmm_rows(const int64_t *rowptr, const int32_t *col, const float *val, int64_t row_lo, int64_t row_hi,
+                                   const float *x, int b, const float *ctl, int coef_slot, const float *z, float *y,
+                                   mmu_stream_t stream) {
     using namespace mmu;
+    const int64_t n = row_hi;
+    MMU_CHECK_ARG(row_lo >= 0 && row_lo <= row_hi, "mmu_block_spmm_rows: bad row range");
     MMU_CHECK_ARG(rowptr && col && val && x && y && ctl, "mmu_block_spmm: null pointer");
     MMU_CHECK_ARG(b == 8 || b == 16 || b == 32, "mmu_block_spmm: block width %d not in {8,16,32}", b);
     MMU_CHECK_ARG(coef_slot >= 0 && coef_slot <= 2, "mmu_block_spmm: coef_slot outside [0,2]");
     MMU_CHECK_ARG(x != y, "mmu_block_spmm: x and y must not alias");
     MMU_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0,
                   "mmu_block_spmm: blocks must be 16-byte aligned");
-    if (n == 0) return MMU_OK;
+    if (n == row_lo) return MMU_OK;
     const float *coef = ctl + (coef_slot == 0 ? BC_COEF_ID : coef_slot == 1 ? BC_COEF1 : BC_COEFK);
     MMU_CHECK_ARG(coef_slot != 2 || z, "mmu_block_spmm: the three-term step needs z");
     const float *zz = z ? z : x;
-    const unsigned blocks = row_group_blocks(n, b);
+    const unsigned blocks = row_group_blocks(n - row_lo, b);
     cudaStream_t st = as_stream(stream);
-    MMU_BLOCK_DISPATCH(b, (spmm_block_kernel<8><<<blocks, 256, 0, st>>>(rowptr, col, val, n, x, coef, zz, y, ctl)),
-                       (spmm_block_kernel<16><<<blocks, 256, 0, st>>>(rowptr, col, val, n, x, coef, zz, y, ctl)),
-                       (spmm_block_kernel<32><<<blocks, 256, 0, st>>>(rowptr, col, val, n, x, coef, zz, y, ctl)));
+    MMU_BLOCK_DISPATCH(b, (spmm_block_kernel<8><<<blocks, 256, 0, st>>>(rowptr, col, val, row_lo, n, x, coef, zz, y, ctl)),
+                       (spmm_block_kernel<16><<<blocks, 256, 0, st>>>(rowptr, col, val, row_lo, n, x, coef, zz, y, ctl)),
+                       (spmm_block_kernel<32><<<blocks, 256, 0, st>>>(rowptr, col, val, row_lo, n, x, coef, zz, y, ctl)));
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }

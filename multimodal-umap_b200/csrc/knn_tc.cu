@@ -380,15 +380,19 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     int t0 = split * p.tiles_per_split + p.window_begin;
     int t1 = min(min(p.n_tiles, (split + 1) * p.tiles_per_split), t0 + p.window_tiles);
     const int32_t *my_list = nullptr;
+    int tstep = 1;
+    // per-block tile sets (pruned search): the splits of a query block take its tiles in turn (split s: tiles s, s + S, ...),
+    // each with its own lists -- a row's neighbours are spread over S x 4 lists by tile parity and column slice
     if (p.tile_list) {
         const int a = qblock < p.n_qblocks ? p.tile_ptr[qblock] : 0, b = qblock < p.n_qblocks ? p.tile_ptr[qblock + 1] : 0;
         my_list = p.tile_list + a;
-        t0 = 0; t1 = b - a;
+        t0 = split; t1 = b - a; tstep = p.n_splits;
     } else if (p.qb_tile_begin) {
-        t0 = qblock < p.n_qblocks ? p.qb_tile_begin[qblock] : 0;
+        t0 = (qblock < p.n_qblocks ? p.qb_tile_begin[qblock] : 0) + split;
         t1 = qblock < p.n_qblocks ? p.qb_tile_end[qblock] : 0;
+        tstep = p.n_splits;
     }
-    const int n_my_tiles = max(0, t1 - t0);
+    const int n_my_tiles = max(0, (t1 - t0 + tstep - 1) / tstep);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_q)) : "memory");
@@ -421,7 +425,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int ti = t0; ti < t1; ++ti) {
+            for (int ti = t0; ti < t1; ti += tstep) {
                 const int t = my_list ? my_list[ti] : ti;
                 for (int kb = 0; kb < p.n_kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -506,7 +510,7 @@ knn_tc_candidates_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         constexpr int COLS = TC_BN / TC_EPI_GROUPS;
         for (int it = 0; it < n_my_tiles; ++it) {
             const int acc = it & 1;
-            const int n0 = (my_list ? my_list[it] : t0 + it) * TC_BN + grp * COLS;
+            const int n0 = (my_list ? my_list[t0 + it * tstep] : t0 + it * tstep) * TC_BN + grp * COLS;
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TC_BN + grp * COLS;
@@ -868,7 +872,7 @@ static TcLayout tc_layout(int64_t n_query, int64_t n_db, int dim, bool shared_op
     // more splits = deeper candidate pool (64 per split): the caller raises min_splits for rows whose
     // neighbourhood gaps are too small for one list to certify
     if (min_splits > best_s) best_s = min_splits;
-    if (min_splits < 0) best_s = 1;                  // pinned to one split (per-block tile sets of the pruned search)
+    if (min_splits < 0) best_s = -min_splits;        // pinned to exactly that many splits (per-block tile sets of the pruned search)
     if (best_s > 8) best_s = 8;
     if (best_s > L.n_tiles) best_s = L.n_tiles;
     L.n_splits = best_s;
@@ -956,7 +960,7 @@ extern "C" int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *d
     cudaStream_t st = as_stream(stream);
     if (stages & 4) MMU_CUDA(cudaMemsetAsync(stats, 0, sizeof(int32_t) * 4, st));
     if (n_query == 0) return MMU_OK;
-    MMU_CHECK_ARG(min_splits >= -1 && min_splits <= 8, "mmu_knn_tc: min_splits outside [-1,8]");
+    MMU_CHECK_ARG(min_splits >= -8 && min_splits <= 8, "mmu_knn_tc: min_splits outside [-8,8]");
     MMU_CHECK_ARG(precision == 0 || precision == 1, "mmu_knn_tc: precision must be 0 (fp16) or 1 (split fp16)");
     const TcLayout L = tc_layout(n_query, n_db, dim, query_is_db != 0, min_splits, precision != 0);
     const int split = precision != 0;
@@ -974,7 +978,7 @@ extern "C" int mmu_knn_tc_ex(const float *query, int64_t n_query, const float *d
     float *cscore = reinterpret_cast<float *>(ws + L.off_cscore);
     float *tau = reinterpret_cast<float *>(ws + L.off_tau);
 
-    MMU_CHECK_ARG(!pruned || L.n_splits == 1, "mmu_knn_tc_ex: per-block tile sets need a single database split (got %d)", L.n_splits);
+    MMU_CHECK_ARG(!pruned || min_splits < 0, "mmu_knn_tc_ex: per-block tile sets need a pinned split count (min_splits < 0)");
     if (stages & 1) {
     // ---- prep
     MMU_CUDA(cudaMemsetAsync(prm, 0, 256, st));

@@ -239,7 +239,7 @@ epoch_tail_peer_kernel(PeerPtrs params, PeerPtrs grads, PeerPtrs flags, const fl
 // with multimem moves half of that), which is why this form is used for small tables only (where latency is the cost).
 // The grid is one block per SM: blocks spin on peers' flags, so all of them have to become resident.
 template <int WT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *__restrict__ grad, float *__restrict__ m,
                        float *__restrict__ v, int64_t n4, int64_t slot4, int world_rt, int rank, double lr, double beta1d,
                        double beta2d, float beta2, float omb1, float omb2, float eps, OptState *__restrict__ st,
@@ -256,18 +256,23 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // ---- A: push my partial gradient to the owners, clear it
+    // ---- A: push my partial gradient to the owners, clear it.  Shard by shard (no per-element owner arithmetic), four
+    // independent local loads in flight per thread before their remote stores
     float4 *g4 = reinterpret_cast<float4 *>(grad);
-    for (int64_t i = tid; i < n4; i += stride) {
-        // owner s of element i: the largest s with n4*s/world <= i
-        int s = (int)(((i + 1) * world - 1) / n4);
-        if (s >= world) s = world - 1;
-        while (s > 0 && n4 * s / world > i) --s;
-        while (s + 1 < world && n4 * (s + 1) / world <= i) ++s;
-        const int64_t lo_s = n4 * s / world;
-        const float4 gv = g4[i];
-        st_peer(reinterpret_cast<float4 *>(inbox.p[s]) + (int64_t)rank * slot4 + (i - lo_s), gv);
-        g4[i] = zero;
+    for (int s = 0; s < world; ++s) {
+        const int64_t lo_s = n4 * s / world, hi_s = n4 * (s + 1) / world;
+        float4 *dst = reinterpret_cast<float4 *>(inbox.p[s]) + (int64_t)rank * slot4 - lo_s;
+        int64_t i = lo_s + tid;
+        for (; i + 3 * stride < hi_s; i += 4 * stride) {
+            const float4 a = g4[i], b = g4[i + stride], c = g4[i + 2 * stride], d = g4[i + 3 * stride];
+            st_peer(dst + i, a); st_peer(dst + i + stride, b); st_peer(dst + i + 2 * stride, c); st_peer(dst + i + 3 * stride, d);
+            g4[i] = zero; g4[i + stride] = zero; g4[i + 2 * stride] = zero; g4[i + 3 * stride] = zero;
+        }
+        for (; i < hi_s; i += stride) {
+            const float4 gv = g4[i];
+            st_peer(dst + i, gv);
+            g4[i] = zero;
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -441,7 +446,7 @@ extern "C" int mmu_epoch_tail_push(const uint64_t *peer_params, const uint64_t *
     OptState *os = reinterpret_cast<OptState *>(state);
     cudaStream_t st = as_stream(stream);
 #define MMU_PUSH(WTV)                                                                                                       \
-    epoch_tail_push_kernel<WTV><<<blocks, 256, 0, st>>>(pp, ib, ff, grad, m, v, n4, slot4, world, rank, lr, beta1, beta2,   \
+    epoch_tail_push_kernel<WTV><<<blocks, 512, 0, st>>>(pp, ib, ff, grad, m, v, n4, slot4, world, rank, lr, beta1, beta2,   \
                                                         (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, \
                                                         os, done_counter, done_counter + 1)
     if (world == 2) MMU_PUSH(2);

@@ -399,11 +399,19 @@ class UMAPMixture:
             syms.append(sym)
             graphs.append(_coo(sym))
         embeds = [None] * len(encoder_indices)
+        from umap_b200 import spectral as SP
         with profiler.stage("spectral_init"):
+            # large graphs: one collective solve with the operator applications sharded by rows (identical result on
+            # every rank, nothing to broadcast); small graphs: modality m on rank m mod W, concurrently, then broadcast
+            collective = [SP.shardable(syms[idx], self.out_dim) for idx in range(len(encoder_indices))]
             for idx, i in enumerate(encoder_indices):
-                if D.rank() == self.encoders[i].id % D.world():
+                if collective[idx]:
+                    embeds[idx] = spectral_init(syms[idx], self.out_dim, shard=True).contiguous()
+                elif D.rank() == self.encoders[i].id % D.world():
                     embeds[idx] = spectral_init(syms[idx], self.out_dim).contiguous()
             for idx, i in enumerate(encoder_indices):
+                if collective[idx]:
+                    continue
                 owner = self.encoders[i].id % D.world()
                 if embeds[idx] is None:
                     embeds[idx] = torch.empty((syms[idx].n_rows, self.out_dim), dtype=torch.float32, device="cuda")

@@ -36,7 +36,9 @@ from .native import check, lib, ptr, stream
 
 last_stats: dict = {}
 SAFETY = 1e-3
-ONE_SPLIT = -1                 # min_splits value that pins the search to a single database split (one 64-entry list per row)
+ONE_SPLIT = -2                 # min_splits value that PINS the split count: two splits take a block's tiles in turn, so a row's
+                               # neighbours are spread over 2 x 4 lists of 16 (by tile parity and column slice); with one split
+                               # 0.6 % of the rows had more than 16 of their 30 neighbours in one list and could not certify
 
 
 def _spread_rows(n: int, count: int, device) -> torch.Tensor:
@@ -68,7 +70,23 @@ def contrast(x: torch.Tensor, k: int, sample: int = 1024) -> float:
 
 
 def farthest_point_centroids(x: torch.Tensor, n_centroids: int, sub_rows: int = 65536) -> torch.Tensor:
-    """Greedy k-centre on a strided subsample: deterministic (no RNG: every rank gets the same centroids)."""
+    """Greedy k-centre on a hashed subsample (mmu_fps_centroids: one persistent kernel, a grid barrier per round):
+    deterministic -- no RNG, every rank gets the same centroids."""
+    n = x.shape[0]
+    sub = x if n <= sub_rows else x.index_select(0, _spread_rows(n, sub_rows, x.device))
+    sub = sub.contiguous()
+    n_centroids = min(n_centroids, sub.shape[0])
+    L = lib()
+    ws = torch.empty(L.mmu_fps_workspace_bytes(sub.shape[0]), dtype=torch.uint8, device=x.device)
+    cent = torch.empty((n_centroids, x.shape[1]), dtype=torch.float32, device=x.device)
+    rows = torch.empty(n_centroids, dtype=torch.int32, device=x.device)
+    check(L.mmu_fps_centroids(ptr(sub), sub.shape[0], x.shape[1], n_centroids, ptr(ws), ws.numel(), ptr(cent), ptr(rows), stream()),
+          "mmu_fps_centroids")
+    return cent
+
+
+def farthest_point_centroids_torch(x: torch.Tensor, n_centroids: int, sub_rows: int = 65536) -> torch.Tensor:
+    """the same selection with torch ops (test reference for the kernel)"""
     n = x.shape[0]
     sub = x if n <= sub_rows else x.index_select(0, _spread_rows(n, sub_rows, x.device))
     d2 = torch.full((sub.shape[0],), float("inf"), device=x.device)
@@ -161,7 +179,7 @@ def knn_pruned(x: torch.Tensor, k: int, n_centroids: int | None = None, max_frac
     check(L.mmu_knn_tc_layout(nq, n, dim, int(same), ONE_SPLIT, precision, words, consts), "mmu_knn_tc_layout")
     words = list(words)
     n_qb, n_splits, n_tiles, kp, bm, bn = words[6], words[7], words[8], words[9], words[10], words[11]
-    if n_splits != 1 or k + 1 > kp:
+    if n_splits != -ONE_SPLIT or k + 1 > kp:
         return None
     idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
     dist = torch.empty((nq, k), dtype=torch.float32, device=dev)

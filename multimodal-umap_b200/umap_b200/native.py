@@ -46,6 +46,8 @@ _SIGNATURES = {
                               c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_knn_tc_layout": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mmu_fps_workspace_bytes": (c_size_t, [c_int64]),
+    "mmu_fps_centroids": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "mmu_knn_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mmu_smooth_knn": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
@@ -63,6 +65,8 @@ _SIGNATURES = {
     "mmu_block_ctl_init": (c_int, [c_void_p, c_void_p]),
     "mmu_block_spmm": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                c_void_p]),
+    "mmu_block_spmm_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_void_p]),
     "mmu_block_gram_workspace_bytes": (c_size_t, [c_int]),
     "mmu_block_gram": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_block_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p,

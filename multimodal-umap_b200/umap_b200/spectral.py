@@ -14,6 +14,7 @@ import os
 
 import torch
 
+from . import dist as D
 from .graph import Graph, spmm, spmm_axpby
 from .native import check, lib, ptr, stream
 
@@ -84,7 +85,8 @@ def block_width(out_dim: int) -> int:
     return 8 if m <= 5 else 16 if m <= 12 else 32 if m <= 24 else -(-(m + 8) // 4) * 4
 
 
-def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 30, degree: int = 10) -> torch.Tensor:
+def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 30, degree: int = 10,
+                            shard: bool = False) -> torch.Tensor:
     """Chebyshev-filtered subspace iteration with EVERY step on the engine's own kernels (csrc/block_eig.cu) and every
     scalar of the iteration (Ritz values, residual, convergence flag, filter edge, Chebyshev coefficients) in a
     device-resident control block: the host enqueues whole outer iterations and reads the flag once per chunk of
@@ -102,10 +104,19 @@ def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter:
     aval = normalized_adjacency(g)
     deg = torch.zeros(n, dtype=torch.float32, device=dev)
     deg.index_add_(0, g.row.long(), g.val)
-    bufs = [torch.empty((n, b), dtype=torch.float32, device=dev) for _ in range(4)]
+    # Multi-GPU, large graphs: the operator applications (all but a few per cent of the solve) are sharded by rows -- rank r
+    # computes rows row_block(r) of every product and the blocks are all-gathered in place (NCCL over NVLink); everything
+    # else is replicated on the identical full blocks, so the ranks' results are bit-identical and nothing is reduced.
+    world, rank = (D.world(), D.rank()) if shard else (1, 0)
+    per = D.block_size(n, world) if world > 1 else n
+    n_alloc = per * world
+    r_lo, r_hi = (min(n, rank * per), min(n, rank * per + per)) if world > 1 else (0, n)
+    bufs = [torch.zeros((n_alloc, b), dtype=torch.float32, device=dev) for _ in range(4)]
     x, ax, y0, y1 = bufs
-    x.copy_(torch.randn((n, b), dtype=torch.float32, device=dev))
-    x[:, 0] = deg.clamp(min=1e-6).sqrt()                    # the known top eigenvector of A
+    x[:n].copy_(torch.randn((n, b), dtype=torch.float32, device=dev))
+    if world > 1:
+        D.broadcast(x, 0)                                   # one start block for all ranks
+    x[:n, 0] = deg.clamp(min=1e-6).sqrt()                   # the known top eigenvector of A
     ctl = torch.empty(L.mmu_block_ctl_words(), dtype=torch.float32, device=dev)
     flag = ctl.view(torch.int32)
     check(L.mmu_block_ctl_init(ptr(ctl), st), "mmu_block_ctl_init")
@@ -132,20 +143,28 @@ def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter:
 
     orthonormalise(x, x, True)
 
+    def spmm(src, slot, z, dst, what):
+        if world == 1:
+            check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(src), b, ptr(ctl), slot, ptr(z), ptr(dst), st), what)
+            return
+        check(L.mmu_block_spmm_rows(rp, col, ptr(aval), r_lo, r_hi, ptr(src), b, ptr(ctl), slot, ptr(z), ptr(dst), st), what)
+        import torch.distributed as tdist
+        tdist.all_gather_into_tensor(dst, dst[rank * per: rank * per + per])          # in place: my block is already there
+
     def outer():
         nonlocal x, ax, y0, y1
-        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(x), b, ptr(ctl), 0, None, ptr(ax), st), "spmm")
+        spmm(x, 0, None, ax, "spmm")
         check(L.mmu_block_gram(ptr(x), ptr(ax), n, b, 1, ptr(ws), ptr(gm), None, ptr(ctl), st), "gram")
         check(L.mmu_eigh_small_flag(ptr(gm), b, ptr(lam), ptr(vm), ptr(flag), st), "eigh")
         # x <- x V, ax <- ax V (Ritz vectors, descending), column residuals |A x_j - theta_j x_j|^2 into the control block
         check(L.mmu_block_rotate(ptr(x), ptr(x), ptr(ax), ptr(ax), n, b, ptr(vm), 1, ptr(lam), ptr(ctl), st), "rotate")
         check(L.mmu_block_ritz(ptr(lam), b, m, tol, max_iter, ptr(ctl), st), "ritz")
         # Chebyshev filter of degree `degree` on [-1, cut]: T_1 from x, T_2 with z = x, then z aliases the output
-        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(x), b, ptr(ctl), 1, None, ptr(y1), st), "cheb1")
-        check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(y1), b, ptr(ctl), 2, ptr(x), ptr(y0), st), "cheb2")
+        spmm(x, 1, None, y1, "cheb1")
+        spmm(y1, 2, x, y0, "cheb2")
         cur, prev = y0, y1
         for _ in range(3, degree + 1):
-            check(L.mmu_block_spmm(rp, col, ptr(aval), n, ptr(cur), b, ptr(ctl), 2, ptr(prev), ptr(prev), st), "chebk")
+            spmm(cur, 2, prev, prev, "chebk")
             cur, prev = prev, cur
         # equalise the column lengths (unit-diagonal Gram) and orthonormalise twice; the result becomes the new block.
         # After convergence every kernel above and below returns at once, so x keeps the converged Ritz vectors.
@@ -163,7 +182,7 @@ def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter:
         chunk = 2
     if os.environ.get("MMUMAP_SPECTRAL_DEBUG") == "1":
         print(f"  chebfsi(device) n={n} b={b}: {iters} Rayleigh-Ritz steps, residual {float(ctl[2]):.3e}, cut {float(ctl[3]):.4f}")
-    vecs = x[:, 1:m]
+    vecs = x[:n, 1:m]
     return (vecs / vecs.norm(dim=0, keepdim=True)).contiguous()
 
 
@@ -232,7 +251,17 @@ def spectral_chebfsi(g: Graph, out_dim: int, tol: float = 3e-4, max_iter: int = 
     return out
 
 
-def spectral_init(g: Graph, out_dim: int, method: str | None = None) -> torch.Tensor:
+SHARD_MIN_ROWS = 400000        # multi-GPU: graphs at least this large shard their operator applications over the ranks
+
+
+def shardable(g: Graph, out_dim: int, method: str | None = None) -> bool:
+    """True when spectral_init(..., shard=True) would run as a collective of all ranks (every rank must then call it)."""
+    method = method or os.environ.get("MMUMAP_SPECTRAL", "chebfsi")
+    return (D.world() > 1 and method == "chebfsi" and block_width(out_dim) in BLOCK_WIDTHS and g.n_rows >= SHARD_MIN_ROWS
+            and os.environ.get("MMUMAP_SPECTRAL_SHARD", "1") == "1")
+
+
+def spectral_init(g: Graph, out_dim: int, method: str | None = None, shard: bool = False) -> torch.Tensor:
     method = method or os.environ.get("MMUMAP_SPECTRAL", "chebfsi")
     if g.n_rows < 3 * (out_dim + 1):
         raise ValueError(f"spectral init needs at least {3 * (out_dim + 1)} points for out_dim={out_dim}")
@@ -241,7 +270,7 @@ def spectral_init(g: Graph, out_dim: int, method: str | None = None) -> torch.Te
     if method == "chebfsi":
         # device-resident form for the instantiated block widths (out_dim <= 23); the torch-assisted form otherwise
         if block_width(out_dim) in BLOCK_WIDTHS:
-            return spectral_chebfsi_device(g, out_dim)
+            return spectral_chebfsi_device(g, out_dim, shard=shard and shardable(g, out_dim, method))
         return spectral_chebfsi(g, out_dim)
     if method == "chebfsi_torch":
         return spectral_chebfsi(g, out_dim)

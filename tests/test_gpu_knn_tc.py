@@ -227,3 +227,23 @@ def test_pruned_search_declines_on_unclustered_data():
     assert knn_pruned.contrast(x, 15) > knn_tc.PRUNE_CONTRAST
     assert knn_pruned.knn_pruned(x, 15, n_centroids=256) is None
     assert knn_pruned.last_stats["visited_tile_fraction"] > 0.5
+
+
+def test_farthest_point_kernel_covers_every_cluster():
+    """mmu_fps_centroids (persistent kernel, grid barrier per round): the first centroids of well separated blobs are
+    one per blob, and the selection equals the torch restatement of the greedy rule wherever the arg-max is not a
+    floating-point near-tie (the two forms sum the squared distances in different orders)."""
+    from umap_b200 import knn_pruned
+    g = torch.Generator(device="cuda").manual_seed(4)
+    blobs, d, n = 37, 48, 20000
+    centres = 6.0 * torch.randn((blobs, d), generator=g, device="cuda")
+    lab = torch.arange(n, device="cuda") % blobs
+    x = (centres[lab] + torch.randn((n, d), generator=g, device="cuda")).contiguous()
+    cent = knn_pruned.farthest_point_centroids(x, 64)
+    ref = knn_pruned.farthest_point_centroids_torch(x, 64)
+    torch.cuda.synchronize()
+    near = torch.cdist(cent[:blobs], centres).argmin(dim=1)
+    assert near.unique().numel() == blobs                       # one centroid in every blob before any blob gets two
+    same = (cent == ref).all(dim=1)
+    assert int(same[:blobs].sum()) >= blobs - 2 and bool(same[0])
+    assert bool(torch.isfinite(cent).all())
