@@ -50,7 +50,10 @@ fps_kernel(const float *__restrict__ sub, int n_sub, int dim, int n_centroids, f
         }
         if (threadIdx.x == 0) {
             s_best = 0ull;
-            if (blockIdx.x == 0) { picked[c] = cur; best[(c + 2) % 3] = 0ull; }     // slot of round c+2: untouched until then
+            // clear the slot of round c+1 now: it was last read right after the barrier of round c-2, and no block can be
+            // in round c before every block has passed the barrier of round c-1, i.e. finished that read; the clear is
+            // visible to every block after this round's barrier.  (The slot of round c-1 may still be being read.)
+            if (blockIdx.x == 0) { picked[c] = cur; best[(c + 1) % 3] = 0ull; }
         }
         __syncthreads();
         unsigned long long mine = 0ull;
