@@ -29,7 +29,7 @@ __device__ __forceinline__ void fps_grid_sync(unsigned int *count, volatile unsi
 }
 
 // bar: [0] arrival counter, [1] generation; best: 3 rotating 64-bit slots {distance bits : ~row} (atomicMax)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 fps_kernel(const float *__restrict__ sub, int n_sub, int dim, int n_centroids, float *__restrict__ d2,
            unsigned long long *__restrict__ best, unsigned int *__restrict__ bar, float *__restrict__ cent,
            int32_t *__restrict__ picked) {
@@ -98,7 +98,8 @@ extern "C" int mmu_fps_centroids(const float *sub, int64_t n_sub, int dim, int n
     int sms = sm_count();
     if (sms <= 0) sms = 148;
     // one block per SM: the grid barrier needs every block resident
-    fps_kernel<<<sms, 256, sizeof(float) * (size_t)dim, st>>>(sub, (int)n_sub, dim, n_centroids, d2, best, bar, out_centroids, out_rows);
+    // 32 warps per SM: a round is a chain of L2-latency-bound row loads per warp, so more warps = fewer rows per warp
+    fps_kernel<<<sms, 1024, sizeof(float) * (size_t)dim, st>>>(sub, (int)n_sub, dim, n_centroids, d2, best, bar, out_centroids, out_rows);
     MMU_LAUNCH_CHECK();
     return MMU_OK;
 }
