@@ -187,6 +187,7 @@ class LayoutOptimizer:
             self.mods[-1].n_batches_norm = int(norm_batches[i]) if norm_batches is not None else self.mods[-1].n_batches
         # approximate ex2/lg2/rcp force arithmetic only where the stream is not the reference's anyway
         self.fast_math = os.environ.get("MMUMAP_FAST_MATH", "1" if self.sample_stream == "device" else "0") == "1"
+        self.peer_tail = os.environ.get("MMUMAP_PEER_TAIL", "auto")      # read once per optimiser, not per epoch
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev) if track_loss else None
         self.losses: list[float] = []
         self.done = 0                  # epochs completed (== the device-side epoch counter)
@@ -376,7 +377,7 @@ class LayoutOptimizer:
             # -> [all parameters delivered] -> clear my gradient buffer
             pr, w, r = self.peer, D.world(), D.rank()
             pr["seq"] += 1
-            tail = os.environ.get("MMUMAP_PEER_TAIL", "auto")
+            tail = self.peer_tail
             if tail == "auto":
                 # small tables: NVLink latency is the cost -> push form (two one-way hops); large tables: the pull form,
                 # whose in-switch reduction (multimem) moves half the bytes
@@ -589,7 +590,7 @@ class LayoutOptimizer:
                      and (D.world() == 1 or (self.peer is None and os.environ.get("MMUMAP_GRAPH_NCCL", "0") == "1")))
         peer_graph = (self.peer is not None and self.sample_stream == "device" and self.loss is None and epochs >= 12
                       and self.mode in ("fit", "transform") and not profiler.enabled(2)
-                      and os.environ.get("MMUMAP_PEER_TAIL", "auto") in ("auto", "fused", "push")
+                      and self.peer_tail in ("auto", "fused", "push")
                       and os.environ.get("MMUMAP_EPOCH_GRAPH", "1") == "1")
         if peer_graph:
             self._run_graphed(epochs)

@@ -64,6 +64,8 @@ def test_fit_and_transform_quality_matches_reference(golden_dir, stream, monkeyp
     for i, name in enumerate(train_d):
         got[f"trust_{name}"] = trustworthiness(train_d[name], model.embeds[i].detach().cpu().numpy(), n_neighbors=15)
     print({k: round(v, 4) for k, v in got.items()}, {k: np.round(ref[k], 4).tolist() for k in got})
+    _record(f"e2e_quality_{stream}_stream", {"engine": {k: float(v) for k, v in got.items()},
+                                            "reference_runs": {k: np.asarray(ref[k], dtype=float).tolist() for k in got}})
     slack = {"similarity": 0.05, "knn1": 0.05, "knn5": 0.05, "trust_texts": 0.02, "trust_images": 0.02}
     for key, val in got.items():
         lo = float(ref[key].mean()) - 3.0 * float(ref[key].std()) - slack[key]
@@ -145,3 +147,17 @@ def test_reference_written_checkpoint_loads_and_transforms(golden_dir):
     model.save_state_dict(tmp)
     again = model_mod.UMAPMixture.load_state_dict(tmp)
     assert torch.equal(again.embeds[0].detach().cpu(), model.embeds[0].detach().cpu())
+
+
+def _record(key, value):
+    """measured metrics go to gpurun_out/quality_tests.json (the builder copies it to profiles/)"""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "quality_tests.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[key] = value
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
