@@ -181,3 +181,47 @@ def test_peer_entry_points_validate_arguments():
     assert b"multiple of 4" in lib.mmu_last_error()
     assert lib.mmu_eigh_small(None, 4, None, None, None) == 1
     assert lib.mmu_eigh_small(p, 65, p, p, None) == 1 and b"n=65" in lib.mmu_last_error()
+
+
+def test_round2_entry_points_validate_arguments():
+    """Argument checks of the round-2 entry points run before any launch (no GPU needed): the staged / pruned kNN call,
+    the record-form optimiser calls, the block eigensolver operations, the epoch tails, the roofs."""
+    from umap_b200 import native
+    lib = native.lib()
+    buf = ctypes.create_string_buffer(4096)
+    p = (ctypes.addressof(buf) + 255) & ~255
+    err = lambda: lib.mmu_last_error()
+    # kNN: stage mask, paired tile arguments, pinned split count for per-block tile sets
+    args = [p, 256, p, 256, 8, 5, 1, 0, None, 1, 0, 0, p, 1 << 30, p, p, p, p]
+    assert lib.mmu_knn_tc_ex(*args, 0, None, None, None, None, 0, None, None) == 1 and b"stages" in err()
+    assert lib.mmu_knn_tc_ex(*args, 7, p, None, None, None, 0, None, None) == 1 and b"pairs" in err()
+    assert lib.mmu_knn_tc_ex(*args, 2, p, p, None, None, 0, None, None) == 1 and b"pinned split count" in err()
+    words = (ctypes.c_int64 * 12)()
+    consts = (ctypes.c_float * 4)()
+    assert lib.mmu_knn_tc_layout(1000, 5000, 128, 0, -2, 1, words, consts) == 0
+    assert words[7] == 2 and words[9] == 64 and words[10] == 128 and words[11] == 256 and consts[0] > 0
+    assert lib.mmu_knn_tc_workspace_bytes(1000, 5000, 128, 0, -2, 1) > int(words[4])
+    # optimiser: record alignment, dimensions
+    assert lib.mmu_edge_forces(p + 4, p, None, p, 1, 8, 10, p, p, p, p, 16, 1.5, 0.9, 0, p, None, 1, 0, None) == 1
+    assert b"16-byte aligned" in err()
+    assert lib.mmu_edge_forces(p, p, None, p, 1, 8, 10, p, p, p, p, 200, 1.5, 0.9, 0, p, None, 1, 0, None) == 1 and b"dim=200" in err()
+    assert lib.mmu_edge_records(p, p, p, -1, 256, p, p, None) == 1
+    assert lib.mmu_edge_sample_range(p, p, p, 5, 3, 256, 1, 0, p, p, p, p, None) == 1 and b"edge range" in err()
+    # block eigensolver operations
+    assert lib.mmu_block_ctl_words() >= 64
+    assert lib.mmu_block_spmm(p, p, p, 10, p, 12, p, 0, None, p + 256, None) == 1 and b"block width 12" in err()
+    assert lib.mmu_block_spmm(p, p, p, 10, p, 8, p, 2, None, p + 256, None) == 1 and b"needs z" in err()
+    assert lib.mmu_block_gram(p, p, 10, 8, 2, p, p, None, None, None) == 1 and b"dinv" in err()
+    assert lib.mmu_block_rotate(p, p, p, None, 10, 8, p, 0, None, None, None) == 1
+    assert lib.mmu_block_ritz(p, 8, 9, 1e-3, 10, p, None) == 1
+    assert lib.mmu_block_gram_workspace_bytes(32) == 4 * 592 * 32 * 32
+    # epoch tails
+    ptrs = (ctypes.c_uint64 * 2)(p, p + 1024)
+    assert lib.mmu_epoch_tail_push(ptrs, ptrs, ptrs, p, p, p, 64, 8, 2, 0, 0.01, 0.9, 0.999, 1e-8, p, p, None) == 1
+    assert b"inbox slot" in err()
+    assert lib.mmu_epoch_tail_peer(ptrs, ptrs, ptrs, 16, 0, p, p, 64, 2, 0, 0, 0.01, 0.9, 0.999, 1e-8, p, p, None) == 1
+    assert b"both multicast" in err()
+    # roofs, farthest-point sampling
+    assert lib.mmu_roof_random_rows(p, p, 100, 3, 1000, 0, 1, 1, p, None) == 1 and b"row_floats" in err()
+    assert lib.mmu_fps_centroids(p, 100, 8, 4, p, 16, p, p, None) == 1 and b"workspace" in err()
+    assert lib.mmu_fps_workspace_bytes(1000) == 4064
