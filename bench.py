@@ -619,6 +619,8 @@ def run_b200(args, workload, data):
                 # the tensor cores evaluate only visited_tile_fraction of it (x3 for the split-fp16 operands), so frac > 1
                 # measures the pruning, not the tensor pipe
                 "pruned_search": pruning,
+                "traffic_note": "DRAM read + write bytes per CANDIDATES-KERNEL launch from the ncu capture (a texts search walks "
+                                "the database in ~48 MB windows: ten launches); `achieved` is per kNN stage call",
                 "share_of_step": knn["ms"] / total_ms if total_ms else None,
                 "ms_per_launch": knn["ms"] / max(knn["calls"], 1), "ncu": kf or None}
     # the force kernel: algorithmic bytes per launch / measured launch time, against the HBM copy peak as

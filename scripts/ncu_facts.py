@@ -34,8 +34,8 @@ FACTS = {
     "launch__registers_per_thread": "registers",
     "launch__grid_size": "grid",
 }
-UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9,
-              "cycle/nsecond": 1e9, "cycle/usecond": 1e6, "cycle/second": 1.0}
+UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9,
+              "hz": 1.0, "Khz": 1e3, "Mhz": 1e6, "Ghz": 1e9}
 
 
 def parse(rep):
