@@ -191,6 +191,18 @@ int mmu_fuzzy_union(const int32_t *col, const float *w, int64_t n, int k, void *
                     size_t workspace_bytes, int64_t *out_rowptr, int32_t *out_row,
                     int32_t *out_col, float *out_val, mmu_stream_t stream);
 
+/* Rows [row_base, row_base + n_rows) of the same union (multi-GPU: SURVEY 8(e), "transpose = exchange of edges keyed by
+ * destination row block, then local sort-merge"): col_block / w_block are those rows of G; in_key / in_src / in_w [n_in]
+ * are the entries of the WHOLE graph whose destination lies in the block, in source-major order, with
+ * in_key = dst - row_base.  The kNN result is replicated after its all-gather, so the exchange step is the host's filter
+ * of that replica; each rank sorts and merges 1/W of the entries and the CSR blocks are all-gathered.  out_rowptr
+ * [n_rows + 1] is LOCAL (starts at 0), out_row holds global row numbers; capacity k * n_rows + n_in entries. */
+size_t mmu_union_rows_workspace_bytes(int64_t n_rows, int64_t n_in);
+int mmu_fuzzy_union_rows(const int32_t *col_block, const float *w_block, int64_t n_rows, int k, const int32_t *in_key,
+                         const int32_t *in_src, const float *in_w, int64_t n_in, int64_t row_base, void *workspace,
+                         size_t workspace_bytes, int64_t *out_rowptr, int32_t *out_row, int32_t *out_col,
+                         float *out_val, mmu_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * K6  transform / invert initialisation    ref: model.py:236-252 (embed_query)
  * out[q] = sum_j (w_qj / max(sum_j w_qj, 1e-6)) * ref[col_qj]

@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256)
 union_write_kernel(const int32_t *__restrict__ col, const float *__restrict__ w, int64_t n, int k,
                    const uint32_t *__restrict__ tptr, const int32_t *__restrict__ tsrc,
                    const float *__restrict__ tw, const int64_t *__restrict__ out_rowptr,
-                   int32_t *__restrict__ out_row, int32_t *__restrict__ out_col, float *__restrict__ out_val) {
+                   int32_t *__restrict__ out_row, int32_t *__restrict__ out_col, float *__restrict__ out_val,
+                   int32_t row_base) {
     __shared__ int32_t As[8][MMU_MAX_K];
     __shared__ int32_t Pf[8][MMU_MAX_K + 1];     // Pf[i] = #flagged A elements with index < i
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -258,7 +259,7 @@ union_write_kernel(const int32_t *__restrict__ col, const float *__restrict__ w,
                 float wb = Bw[lb[h]];
                 v = __fsub_rn(__fadd_rn(wa[h], wb), __fmul_rn(wa[h], wb));   // ref: model.py:271
             }
-            out_row[pos] = (int32_t)r;
+            out_row[pos] = (int32_t)r + row_base;
             out_col[pos] = a[h];
             out_val[pos] = v;
         }
@@ -273,7 +274,7 @@ union_write_kernel(const int32_t *__restrict__ col, const float *__restrict__ w,
         }
         if (lo < k && As[wl][lo] == b) continue;
         int64_t pos = obase + lo + j - Pf[wl][lo];
-        out_row[pos] = (int32_t)r;
+        out_row[pos] = (int32_t)r + row_base;
         out_col[pos] = b;
         out_val[pos] = Bw[j];
     }
@@ -287,9 +288,11 @@ struct UnionPlan {
     size_t off_key[2], off_src[2], off_w[2], off_hist, off_partial, off_indeg, off_tptr, off_cnt, total;
 };
 
-static UnionPlan make_plan(int64_t n, int k) {
+static UnionPlan make_plan_items(int64_t n, int64_t items);
+static UnionPlan make_plan(int64_t n, int k) { return make_plan_items(n, n * (int64_t)k); }
+static UnionPlan make_plan_items(int64_t n, int64_t items) {
     UnionPlan p;
-    p.items = n * (int64_t)k;
+    p.items = items > 0 ? items : 1;
     p.n_tiles = (p.items + RS_TILE - 1) / RS_TILE;
     p.bits = 1;
     while (((int64_t)1 << p.bits) < n) ++p.bits;
@@ -377,7 +380,73 @@ extern "C" int mmu_fuzzy_union(const int32_t *col, const float *w, int64_t n, in
     union_count_kernel<<<wblocks, 256, 0, st>>>(col, n, k, tptr, tsrc, cnt);
     rc = exclusive_scan<uint32_t, int64_t>(cnt, n, out_rowptr, partial64, 1, st);
     if (rc) return rc;
-    union_write_kernel<<<wblocks, 256, 0, st>>>(col, w, n, k, tptr, tsrc, tw, out_rowptr, out_row, out_col, out_val);
+    union_write_kernel<<<wblocks, 256, 0, st>>>(col, w, n, k, tptr, tsrc, tw, out_rowptr, out_row, out_col, out_val, 0);
+    MMU_LAUNCH_CHECK_N(3);
+    return MMU_OK;
+}
+
+// ------------------------------------------------------------------ row block of the union (multi-GPU)
+// Rows [row_base, row_base + n_rows) of S = G + G^T - G*G^T from (a) the block's own rows of G (col_block / w_block,
+// fixed degree k) and (b) the in-edges of the block: the entries (src, dst, w) of the WHOLE graph with dst inside the block,
+// in src-major order, given as in_key = dst - row_base, in_src, in_w (n_in of them; the host filters them out of the
+// replicated kNN result).  Same sort + merge as mmu_fuzzy_union on 1/W of the entries; the ranks' blocks are all-gathered.
+extern "C" size_t mmu_union_rows_workspace_bytes(int64_t n_rows, int64_t n_in) {
+    if (n_rows <= 0) return 0;
+    return mmu::make_plan_items(n_rows, n_in).total;
+}
+
+extern "C" int mmu_fuzzy_union_rows(const int32_t *col_block, const float *w_block, int64_t n_rows, int k, const int32_t *in_key,
+                                    const int32_t *in_src, const float *in_w, int64_t n_in, int64_t row_base, void *workspace,
+                                    size_t workspace_bytes, int64_t *out_rowptr, int32_t *out_row, int32_t *out_col,
+                                    float *out_val, mmu_stream_t stream) {
+    using namespace mmu;
+    MMU_CHECK_ARG(col_block && w_block && workspace && out_rowptr && out_row && out_col && out_val, "mmu_fuzzy_union_rows: null pointer");
+    MMU_CHECK_ARG(n_in == 0 || (in_key && in_src && in_w), "mmu_fuzzy_union_rows: null in-edge arrays");
+    MMU_CHECK_ARG(k >= 1 && k <= MMU_MAX_K, "mmu_fuzzy_union_rows: k=%d outside [1,%d]", k, MMU_MAX_K);
+    MMU_CHECK_ARG(n_rows >= 1 && n_in >= 0 && n_in < (int64_t)1 << 31 && row_base >= 0 && row_base + n_rows < (int64_t)1 << 31,
+                  "mmu_fuzzy_union_rows: bad sizes");
+    UnionPlan p = make_plan_items(n_rows, n_in);
+    MMU_CHECK_ARG(workspace_bytes >= p.total, "mmu_fuzzy_union_rows: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+    cudaStream_t st = as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    int32_t *key[2] = {reinterpret_cast<int32_t *>(ws + p.off_key[0]), reinterpret_cast<int32_t *>(ws + p.off_key[1])};
+    int32_t *src[2] = {reinterpret_cast<int32_t *>(ws + p.off_src[0]), reinterpret_cast<int32_t *>(ws + p.off_src[1])};
+    float *wv[2] = {reinterpret_cast<float *>(ws + p.off_w[0]), reinterpret_cast<float *>(ws + p.off_w[1])};
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ws + p.off_hist);
+    uint32_t *partial32 = reinterpret_cast<uint32_t *>(ws + p.off_partial);
+    int64_t *partial64 = reinterpret_cast<int64_t *>(ws + p.off_partial);
+    uint32_t *indeg = reinterpret_cast<uint32_t *>(ws + p.off_indeg);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(ws + p.off_tptr);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(ws + p.off_cnt);
+    const int32_t *kin = in_key;
+    const int32_t *sin = in_src;
+    const float *win = in_w;
+    if (n_in > 0) {
+        unsigned rs_blocks = (unsigned)((p.n_tiles + RS_WARPS - 1) / RS_WARPS);
+        size_t rs_smem = sizeof(uint32_t) * RS_WARPS * p.bins;
+        int cur = 0;
+        for (int pass = 0; pass < p.passes; ++pass) {
+            int shift = pass * p.width;
+            radix_hist_kernel<<<rs_blocks, RS_WARPS * 32, rs_smem, st>>>(kin, n_in, shift, p.bins, p.n_tiles, hist);
+            int rc = exclusive_scan<uint32_t, uint32_t>(hist, (int64_t)p.bins * p.n_tiles, hist, partial32, 0, st);
+            if (rc) return rc;
+            radix_scatter_kernel<false><<<rs_blocks, RS_WARPS * 32, rs_smem, st>>>(kin, sin, win, n_in, k, shift, p.bins, p.n_tiles,
+                                                                                  hist, key[cur], src[cur], wv[cur]);
+            MMU_LAUNCH_CHECK_N(2);
+            kin = key[cur]; sin = src[cur]; win = wv[cur];
+            cur ^= 1;
+        }
+    }
+    MMU_CUDA(cudaMemsetAsync(indeg, 0, sizeof(uint32_t) * (n_rows + 1), st));
+    if (n_in > 0) indeg_kernel<<<(unsigned)((n_in + 255) / 256), 256, 0, st>>>(in_key, n_in, indeg);
+    int rc = exclusive_scan<uint32_t, uint32_t>(indeg, n_rows, tptr, partial32, 1, st);
+    if (rc) return rc;
+    unsigned wblocks = (unsigned)((n_rows * 32 + 255) / 256);
+    union_count_kernel<<<wblocks, 256, 0, st>>>(col_block, n_rows, k, tptr, sin ? sin : col_block, cnt);
+    rc = exclusive_scan<uint32_t, int64_t>(cnt, n_rows, out_rowptr, partial64, 1, st);
+    if (rc) return rc;
+    union_write_kernel<<<wblocks, 256, 0, st>>>(col_block, w_block, n_rows, k, tptr, sin ? sin : col_block, win ? win : w_block,
+                                                out_rowptr, out_row, out_col, out_val, (int32_t)row_base);
     MMU_LAUNCH_CHECK_N(3);
     return MMU_OK;
 }

@@ -183,10 +183,79 @@ def invert_weights(idx: torch.Tensor, dist: torch.Tensor, a: float, b: float):
     return col, w
 
 
+UNION_SHARD_MIN_EDGES = 4_000_000      # multi-GPU: graphs at least this large build the union one row block per rank
+
+
+def fuzzy_union_rows(col: torch.Tensor, w: torch.Tensor, lo: int, hi: int):
+    """Rows [lo, hi) of the union as (rowptr_local int64 [hi-lo+1], row, col, val): the block's own rows of G plus the
+    in-edges of the block filtered out of the replicated graph (source-major order), mmu_fuzzy_union_rows."""
+    n, k = col.shape
+    dev = col.device
+    flat = col.reshape(-1)
+    e = ((flat >= lo) & (flat < hi)).nonzero(as_tuple=True)[0]                  # ascending entry number = source-major
+    in_key = (flat.index_select(0, e) - lo).to(torch.int32).contiguous()
+    in_src = (e // k).to(torch.int32).contiguous()
+    in_w = w.reshape(-1).index_select(0, e).contiguous()
+    n_in = int(e.numel())
+    nb = hi - lo
+    ws_bytes = lib().mmu_union_rows_workspace_bytes(nb, n_in)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = nb * k + n_in
+    rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+    orow = torch.empty(cap, dtype=torch.int32, device=dev)
+    ocol = torch.empty(cap, dtype=torch.int32, device=dev)
+    oval = torch.empty(cap, dtype=torch.float32, device=dev)
+    cb, wb = col[lo:hi].contiguous(), w[lo:hi].contiguous()
+    check(lib().mmu_fuzzy_union_rows(ptr(cb), ptr(wb), nb, k, ptr(in_key), ptr(in_src), ptr(in_w), n_in, lo, ptr(ws), ws_bytes,
+                                     ptr(rowptr), ptr(orow), ptr(ocol), ptr(oval), stream()), "mmu_fuzzy_union_rows")
+    nnz = int(rowptr[-1].item())
+    return rowptr, orow[:nnz], ocol[:nnz], oval[:nnz]
+
+
+def fuzzy_union_sharded(col: torch.Tensor, w: torch.Tensor) -> Graph:
+    """Multi-GPU union: rank r builds the rows row_block(r) of S -- the exchange of edges keyed by destination
+    row block is the filter of the replicated kNN result -- and the CSR blocks are all-gathered (padded to the largest)."""
+    import torch.distributed as tdist
+    n, k = col.shape
+    dev = col.device
+    world, rank = D.world(), D.rank()
+    lo, hi = D.row_block(n, rank, world)
+    if hi > lo:
+        rp, r_, c_, v_ = fuzzy_union_rows(col, w, lo, hi)
+    else:
+        rp = torch.zeros(1, dtype=torch.int64, device=dev)
+        r_ = torch.zeros(0, dtype=torch.int32, device=dev)
+        c_, v_ = r_.clone(), torch.zeros(0, dtype=torch.float32, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([r_.numel()], dtype=torch.int64, device=dev)
+    tdist.all_gather_into_tensor(counts, mine)
+    counts_h = counts.tolist()
+    mx = max(max(counts_h), 1)
+
+    def gather(t):
+        pad = torch.zeros(mx, dtype=t.dtype, device=dev)
+        pad[: t.numel()] = t
+        full = torch.empty(world * mx, dtype=t.dtype, device=dev)
+        tdist.all_gather_into_tensor(full, pad)
+        return torch.cat([full[i * mx: i * mx + counts_h[i]] for i in range(world)])
+
+    row, colo, val = gather(r_), gather(c_), gather(v_)
+    per = D.block_size(n, world)
+    cnt_pad = torch.zeros(per, dtype=torch.int64, device=dev)
+    cnt_pad[: hi - lo] = rp[1:] - rp[:-1]
+    cnt_all = torch.empty(world * per, dtype=torch.int64, device=dev)
+    tdist.all_gather_into_tensor(cnt_all, cnt_pad)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(cnt_all[:n], 0)
+    return Graph(n, n, rowptr, row, colo, val)
+
+
 def fuzzy_union(col: torch.Tensor, w: torch.Tensor) -> Graph:
     """K5 (ref: model.py:271): S = G + G^T - G*G^T for the fixed-degree graph (col, w) [n x k]."""
     n, k = col.shape
     dev = col.device
+    if D.world() > 1 and n * k >= UNION_SHARD_MIN_EDGES and os.environ.get("MMUMAP_UNION_SHARD", "1") == "1":
+        return fuzzy_union_sharded(col, w)
     ws_bytes = lib().mmu_union_workspace_bytes(n, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     cap = 2 * n * k

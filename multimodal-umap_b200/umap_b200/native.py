@@ -55,6 +55,9 @@ _SIGNATURES = {
     "mmu_union_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "mmu_fuzzy_union": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    "mmu_union_rows_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "mmu_fuzzy_union_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                     c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmu_embed_query": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_spmm_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "mmu_spmm_csr_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_float, c_float, c_void_p,

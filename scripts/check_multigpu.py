@@ -28,7 +28,14 @@ for mode in ("rows", "ring"):
     print(f"[rank {rank}] kNN dist mode {mode}: bit-exact vs single GPU = {ok}", flush=True)
     assert ok
 col, w, _, _ = G.smooth_knn(ref_i, ref_d)
-sym = G.fuzzy_union(col, w)
+os.environ["MMUMAP_UNION_SHARD"] = "0"
+sym = G.fuzzy_union(col, w)                      # replicated (single-GPU kernel on every rank)
+os.environ["MMUMAP_UNION_SHARD"] = "1"
+sh = G.fuzzy_union_sharded(col, w)               # one row block per rank + all-gather
+ok = all(bool(torch.equal(a, b)) for a, b in ((sh.rowptr, sym.rowptr), (sh.row, sym.row), (sh.col, sym.col),
+                                              (sh.val.view(torch.int32), sym.val.view(torch.int32))))
+print(f"[rank {rank}] sharded fuzzy union bit-exact vs the single-GPU union = {ok}", flush=True)
+assert ok
 y0 = torch.randn((n, 16), generator=g, device="cuda") * 0.01
 y1 = torch.randn((n // 2, 16), generator=g, device="cuda") * 0.01
 xh = x[: n // 2].contiguous()

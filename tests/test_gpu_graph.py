@@ -261,3 +261,25 @@ def test_spmm_axpby_all_forms(m):
     out = zt.clone()
     G.spmm_axpby(g, g.val, xt, 2.0, 0.5, out, -1.0, out=out)       # z aliases the output
     assert np.allclose(out.cpu().numpy(), 2.0 * ax + 0.5 * x - z, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,k,blocks", [(5000, 15, 3), (1300, 30, 4), (700, 5, 7)])
+def test_union_row_blocks_concatenate_to_the_full_union(n, k, blocks):
+    """mmu_fuzzy_union_rows (the per-rank share of the multi-GPU union) on consecutive row blocks, in-edges
+    filtered out of the full graph: rowptr, indices and value bits concatenate to exactly what mmu_fuzzy_union gives."""
+    from umap_b200 import graph as G
+    rng = np.random.default_rng(n + k)
+    x = torch.from_numpy(rng.standard_normal((n, 12)).astype(np.float32)).cuda()
+    idx, dist = G.knn_graph(x, x, k, True)
+    col, w, _, _ = G.smooth_knn(idx, dist, "bisect")
+    full = G.fuzzy_union(col, w)
+    cuts = [n * i // blocks for i in range(blocks + 1)]
+    cuts[1] = max(1, cuts[1] - 37) if blocks > 2 else cuts[1]          # uneven blocks
+    rows, cols, vals, counts = [], [], [], []
+    for lo, hi in zip(cuts, cuts[1:]):
+        rp, r_, c_, v_ = G.fuzzy_union_rows(col, w, lo, hi)
+        assert int(rp[0]) == 0 and rp.numel() == hi - lo + 1
+        rows.append(r_); cols.append(c_); vals.append(v_); counts.append(rp[1:] - rp[:-1])
+    assert torch.equal(torch.cat(rows), full.row) and torch.equal(torch.cat(cols), full.col)
+    assert torch.equal(torch.cat(vals).view(torch.int32), full.val.view(torch.int32))
+    assert torch.equal(torch.cumsum(torch.cat(counts), 0), full.rowptr[1:])
