@@ -274,6 +274,9 @@ edge_forces_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict_
     }
 }
 
+#ifndef MMU_STAGED_WIN_BPS
+#define MMU_STAGED_WIN_BPS 4
+#endif
 // ------------------------------------------------------------------ K7b, staged run form (default)
 // FAST selects s^b = ex2(b*lg2(s)) and an approximate reciprocal (device sample stream); !FAST keeps
 // powf/div exactly as the loop version (host-replayed stream, parity tests).
@@ -334,8 +337,12 @@ struct StageCfg {
 // resident, DRAM sees each table once per pass, and the kept records stream through.  The negatives are counter
 // based (Philox keyed on the edge position), so every pass regenerates the same draws: the same pairs, the same
 // arithmetic as the single pass -- only the order of the atomics changes.
+// blocks per SM: the windowed small-row form (LANES == 1: d = 2, 4) is issue bound with a third of the warp slots in use
+// (ncu r02: issue active 69 %, warps active 33 %), so it runs four blocks per SM (<= 64 registers); the others three
+constexpr int staged_blocks_per_sm(int lanes, bool win) { return (lanes == 1 && win) ? MMU_STAGED_WIN_BPS : 3; }
+
 template <int VEC, int LANES, int R, bool FAST, bool WIN>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, staged_blocks_per_sm(LANES, WIN))
 edge_forces_staged_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict__ kept_hdr,
                           const int32_t *__restrict__ neg, const int32_t *__restrict__ batch_kept, int n_batches,
                           uint32_t rep_count, const float *__restrict__ head, const float *__restrict__ tail,
@@ -1064,9 +1071,9 @@ extern "C" int mmu_edge_forces(const int32_t *kept_rec, const int32_t *kept_hdr,
         MMU_LAUNCH_CHECK();
         return MMU_OK;
     }
-    // staged run form: 3 blocks per SM (__launch_bounds__(256, 3)), a grid of whole waves
-    const unsigned blocks = persistent_blocks(256, 3);
+    // staged run form: a grid of whole waves at the kernel's occupancy (__launch_bounds__)
     const bool windows = window_rows > 0 && window_rows < rep_count;
+    const unsigned blocks = persistent_blocks(256, staged_blocks_per_sm(dim <= 4 ? 1 : 2, windows));
     const int n_windows = windows ? (int)((rep_count + window_rows - 1) / window_rows) : 1;
 #define MMU_STAGED(V, L, RR, FASTV, WINV)                                                                        \
     edge_forces_staged_kernel<V, L, RR, FASTV, WINV><<<blocks, 256, 0, st>>>(                                     \
