@@ -275,7 +275,7 @@ edge_forces_kernel(const int4 *__restrict__ kept_rec, const int32_t *__restrict_
 }
 
 #ifndef MMU_STAGED_WIN_BPS
-#define MMU_STAGED_WIN_BPS 4
+#define MMU_STAGED_WIN_BPS 3      // 4 (<= 64 registers, no spills) measured 10.66 against 10.51 ms/epoch on 10M x 2-D: no gain
 #endif
 // ------------------------------------------------------------------ K7b, staged run form (default)
 // FAST selects s^b = ex2(b*lg2(s)) and an approximate reciprocal (device sample stream); !FAST keeps
@@ -337,8 +337,8 @@ struct StageCfg {
 // resident, DRAM sees each table once per pass, and the kept records stream through.  The negatives are counter
 // based (Philox keyed on the edge position), so every pass regenerates the same draws: the same pairs, the same
 // arithmetic as the single pass -- only the order of the atomics changes.
-// blocks per SM: the windowed small-row form (LANES == 1: d = 2, 4) is issue bound with a third of the warp slots in use
-// (ncu r02: issue active 69 %, warps active 33 %), so it runs four blocks per SM (<= 64 registers); the others three
+// blocks per SM.  The windowed small-row form (LANES == 1: d = 2, 4) is issue bound with a third of the warp slots in use
+// (ncu r02: issue active 69 %, warps active 33 %); a fourth block per SM was tried for it and did not pay (see above)
 constexpr int staged_blocks_per_sm(int lanes, bool win) { return (lanes == 1 && win) ? MMU_STAGED_WIN_BPS : 3; }
 
 template <int VEC, int LANES, int R, bool FAST, bool WIN>
