@@ -58,6 +58,8 @@ int mmu_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
  *   "sgd_window_mb" (env MMUMAP_SGD_WINDOW_MB,  default -1) host hint for mmu_edge_forces' window_rows (-1 = automatic)
  *   "knn_fold_norms" (env MMUMAP_KNN_FOLD_NORMS, default 1) 0 = add |Y|^2 in the epilogue instead of inside the contraction
  *   "tail_blocks_per_sm" (env MMUMAP_TAIL_BLOCKS_PER_SM, default 1) grid of mmu_epoch_tail_peer in blocks per SM
+ *   "tail_skip_mask" (env MMUMAP_TAIL_SKIP_MASK, default 0) MEASUREMENT ONLY (results are wrong when set): bit 0 drops the
+ *                   gradient push of mmu_epoch_tail_push, bit 1 its shard step -- what is left is the synchronisation cost
  * Unknown names return MMU_ERR_ARG. */
 int mmu_set_option(const char *name, int64_t value);
 int mmu_get_option(const char *name, int64_t *value);

@@ -61,6 +61,7 @@ static OptionEntry g_options[OPT_COUNT] = {
     {"sgd_window_mb", "MMUMAP_SGD_WINDOW_MB", -1},     // -1: automatic (tables beyond L2), 0: never, >0: p+g bytes per tail window
     {"knn_fold_norms", "MMUMAP_KNN_FOLD_NORMS", 1},    // 1: |Y|^2 and -2 folded into the contraction where supported
     {"tail_blocks_per_sm", "MMUMAP_TAIL_BLOCKS_PER_SM", 1},   // grid of the fused multi-GPU epoch tail, blocks per SM
+    {"tail_skip_mask", "MMUMAP_TAIL_SKIP_MASK", 0},           // MEASUREMENT ONLY: 1 = push tail without the gradient push, 2 = without the shard step
 };
 struct OptionInit {
     OptionInit() {

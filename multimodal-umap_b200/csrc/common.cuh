@@ -51,7 +51,7 @@ bool first_use_on_device(int site);                  // true exactly once per (s
 void note_kernel(int site, const char *fmt, ...);    // name of the kernel variant the site launched last
 
 // A/B switches: read from the environment once at load, changed with mmu_set_option (never getenv per launch)
-enum : int { OPT_FORCE_STAGED = 0, OPT_KNN_CTA_PAIRS, OPT_KNN_WINDOW_MB, OPT_SGD_WINDOW_MB, OPT_KNN_FOLD_NORMS, OPT_TAIL_BLOCKS_PER_SM, OPT_COUNT };
+enum : int { OPT_FORCE_STAGED = 0, OPT_KNN_CTA_PAIRS, OPT_KNN_WINDOW_MB, OPT_SGD_WINDOW_MB, OPT_KNN_FOLD_NORMS, OPT_TAIL_BLOCKS_PER_SM, OPT_TAIL_SKIP_MASK, OPT_COUNT };
 long long option(int id);
 
 static inline cudaStream_t as_stream(mmu_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(512)
 epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *__restrict__ grad, float *__restrict__ m,
                        float *__restrict__ v, int64_t n4, int64_t slot4, int world_rt, int rank, double lr, double beta1d,
                        double beta2d, float beta2, float omb1, float omb2, float eps, OptState *__restrict__ st,
-                       unsigned int *__restrict__ done_counter, uint32_t *__restrict__ seq_word) {
+                       unsigned int *__restrict__ done_counter, uint32_t *__restrict__ seq_word, int skip_mask) {
+    // skip_mask (measurement only, option tail_skip_mask; results are then wrong): 1 = no gradient push, 2 = no shard step
     const int world = WT ? WT : world_rt;
     const uint32_t seq = *seq_word + 1u;
     __shared__ float s_step[2];
@@ -259,7 +260,7 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
     // ---- A: push my partial gradient to the owners, clear it.  Shard by shard (no per-element owner arithmetic), four
     // independent local loads in flight per thread before their remote stores
     float4 *g4 = reinterpret_cast<float4 *>(grad);
-    for (int s = 0; s < world; ++s) {
+    for (int s = 0; s < ((skip_mask & 1) ? 0 : world); ++s) {
         const int64_t lo_s = n4 * s / world, hi_s = n4 * (s + 1) / world;
         float4 *dst = reinterpret_cast<float4 *>(inbox.p[s]) + (int64_t)rank * slot4 - lo_s;
         int64_t i = lo_s + tid;
@@ -292,7 +293,7 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv), bc2_sqrt), eps);
         pp = __fadd_rn(pp, __fdiv_rn(__fmul_rn(neg_step, mm), denom));
     };
-    const int64_t lo4 = n4 * rank / world, hi4 = n4 * (rank + 1) / world;
+    const int64_t lo4 = n4 * rank / world, hi4 = (skip_mask & 2) ? n4 * rank / world : n4 * (rank + 1) / world;
     const float4 *in4 = reinterpret_cast<const float4 *>(inbox.p[rank]);
     for (int64_t i = lo4 + tid; i < hi4; i += stride) {
         float4 gg = ld_peer(in4 + (i - lo4));                                   // slot 0; L1 may hold last epoch's line
@@ -448,7 +449,7 @@ extern "C" int mmu_epoch_tail_push(const uint64_t *peer_params, const uint64_t *
 #define MMU_PUSH(WTV)                                                                                                       \
     epoch_tail_push_kernel<WTV><<<blocks, 512, 0, st>>>(pp, ib, ff, grad, m, v, n4, slot4, world, rank, lr, beta1, beta2,   \
                                                         (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, \
-                                                        os, done_counter, done_counter + 1)
+                                                        os, done_counter, done_counter + 1, (int)option(OPT_TAIL_SKIP_MASK))
     if (world == 2) MMU_PUSH(2);
     else if (world == 4) MMU_PUSH(4);
     else if (world == 8) MMU_PUSH(8);

@@ -22,9 +22,13 @@ def tiny_graph(n):
 rows = [158915, 31783]
 embeds = [torch.randn((n, 16), device="cuda") * 0.01 for n in rows]
 graphs = [tiny_graph(n) for n in rows]
-for label, env, per_sm in (("push", {"MMUMAP_PEER_TAIL": "push"}, 1), ("fused multimem 1/SM", {"MMUMAP_PEER_TAIL": "fused"}, 1), ("fused peer loads 1/SM", {"MMUMAP_PEER_TAIL": "fused", "MMUMAP_PEER_MULTIMEM": "0"}, 1),
+for label, env, per_sm in (("push", {"MMUMAP_PEER_TAIL": "push"}, 1), ("push, no gradient push [timing only]", {"MMUMAP_PEER_TAIL": "push", "_skip": "1"}, 1),
+                           ("push, no shard step [timing only]", {"MMUMAP_PEER_TAIL": "push", "_skip": "2"}, 1),
+                           ("push, barriers only [timing only]", {"MMUMAP_PEER_TAIL": "push", "_skip": "3"}, 1), ("fused multimem 1/SM", {"MMUMAP_PEER_TAIL": "fused"}, 1), ("fused peer loads 1/SM", {"MMUMAP_PEER_TAIL": "fused", "MMUMAP_PEER_MULTIMEM": "0"}, 1),
                            ("legacy 5 launches", {"MMUMAP_PEER_TAIL": "legacy"}, 1)):
     os.environ.pop("MMUMAP_PEER_TAIL", None)
+    env = dict(env)
+    native.set_option("tail_skip_mask", int(env.pop("_skip", "0")))
     os.environ.update(env)
     native.set_option("tail_blocks_per_sm", per_sm)
     import umap_b200.layout as LY
@@ -40,7 +44,7 @@ for label, env, per_sm in (("push", {"MMUMAP_PEER_TAIL": "push"}, 1), ("fused mu
         opt._adam_tail()
     e1.record(); torch.cuda.synchronize()
     if rank == 0:
-        print(f"{world} GPUs, {label:24s} {native.last_kernel('epoch_tail') or 'barrier + adam_peer + barrier + clear':42s} {e0.elapsed_time(e1) / 300 * 1e3:7.1f} us per tail", flush=True)
+        print(f"{world} GPUs, {label:40s} {native.last_kernel('epoch_tail') or 'barrier + adam_peer + barrier + clear':42s} {e0.elapsed_time(e1) / 300 * 1e3:7.1f} us per tail", flush=True)
     dist.barrier()
     os.environ.pop("MMUMAP_PEER_MULTIMEM", None)
     if "MMUMAP_PEER_MULTIMEM" in env:
