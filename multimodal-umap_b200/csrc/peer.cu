@@ -201,10 +201,12 @@ epoch_tail_peer_kernel(PeerPtrs params, PeerPtrs grads, PeerPtrs flags, const fl
         }
     }
     // grid-wide completion: the last block to arrive signals the peers
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                     // the CTA's stores happen-before thread 0's fence through the barrier (cumulativity)
     __shared__ unsigned int s_last;
-    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
         __threadfence_system();
@@ -249,11 +251,6 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
     const uint32_t seq = *seq_word + 1u;
     __shared__ float s_step[2];
     __shared__ unsigned int s_last;
-    if (threadIdx.x == 0) {
-        const uint32_t step = st->step + 1;
-        s_step[0] = (float)(lr / (1.0 - pow(beta1d, (double)step)));
-        s_step[1] = (float)sqrt(1.0 - pow(beta2d, (double)step));
-    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,8 +272,8 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
             g4[i] = zero;
         }
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                 // the CTA's stores happen-before thread 0's fence through the barrier (cumulativity)
+    if (threadIdx.x == 0) __threadfence_system();
     if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
@@ -284,6 +281,11 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
         flags_arrive(flags, world, rank, 0, seq);
     }
     // ---- B: my shard is complete in my inbox once every rank has raised slot 0
+    if (threadIdx.x == 64) {             // (another warp than the one polling: the double-precision pow overlaps the wait)
+        const uint32_t step = st->step + 1;
+        s_step[0] = (float)(lr / (1.0 - pow(beta1d, (double)step)));
+        s_step[1] = (float)sqrt(1.0 - pow(beta2d, (double)step));
+    }
     if (threadIdx.x < 32) flags_wait(flags, world, rank, 0, seq);
     __syncthreads();
     const float neg_step = -s_step[0], bc2_sqrt = s_step[1];
@@ -311,8 +313,8 @@ epoch_tail_push_kernel(PeerPtrs params, PeerPtrs inbox, PeerPtrs flags, float *_
         reinterpret_cast<float4 *>(v)[i] = vv;
         for (int w = 0; w < world; ++w) st_peer(reinterpret_cast<float4 *>(params.p[w]) + i, pp);
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                 // the CTA's stores happen-before thread 0's fence through the barrier (cumulativity)
+    if (threadIdx.x == 0) __threadfence_system();
     if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == 2u * gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
