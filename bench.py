@@ -28,6 +28,7 @@ The JSON line printed by rank 0:
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -119,7 +120,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int = 0, period_s: float = 0.1):
+    def __init__(self, gpu_index: int = 0, period_s: float = 0.025):
         self.gpu_index, self.period = gpu_index, period_s
         self.samples = []          # (sm_mhz, max_mhz, power_w, reasons_bitmask)
         self.thread = self.proc = self.path = None
@@ -129,7 +130,7 @@ class ClockSampler:
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+                mx = self._max_mhz
                 pw = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
@@ -138,20 +139,29 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation, BEFORE the warm-up steps: nvmlInit takes driver-wide locks for tens to hundreds of
+        milliseconds, and run inside the timed region (as start() used to) it stalled the launches of the first
+        timed step's kNN stage -- the sampler must not perturb what it observes."""
         try:
-            import threading
             import pynvml as nv
             nv.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(visible.split(",")[self.gpu_index]) if visible and visible.split(",")[0].isdigit() else self.gpu_index
-            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM))
             self._nv = nv
-            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+        except Exception:
+            self._nv = None
+
+    def start(self):
+        if getattr(self, "_nv", "unset") == "unset":
+            self.prepare()
+        if self._nv is not None:
+            import threading
+            self.thread = threading.Thread(target=self._nvml_loop, args=(self._nv, self._handle), daemon=True)
             self.thread.start()
             return
-        except Exception:
-            self.thread = None
         try:
             self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(
@@ -202,7 +212,9 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s_ for s_, p_ in zip(sm, power) if p_ > 0.5 * max(power)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+        # sm_mhz_min: the tensor-bound kNN stage is ~40 ms of a ~220 ms step and is the one the power cap slows (it
+        # starts right after the previous fit's optimiser has held the board near its limit); the median hides it
+        return {"sm_mhz": statistics.median(busy), "sm_mhz_min": min(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "power_w_max": max(power), "samples": len(sm)}
 
 
@@ -455,9 +467,16 @@ def run_b200(args, workload, data):
     # Spin-up, then the W warm-up steps: a fresh box needs a few seconds of load before clocks and power state
     # settle (the first process on a box measured its kNN stage up to 2x slower during its first ~2 s); untimed
     # fits until rank 0 has seen SPINUP_S seconds of them, the same number on every rank
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.prepare()
+    # The warm-up holds the previous fit's model while the next one runs, exactly as the timed loop does: with the
+    # result discarded instead, the caching allocator met a new lifetime pattern in timed steps 2-3 and its
+    # cudaMalloc/cudaFree calls landed inside those steps' kNN stage (single searches of 108 ms instead of 31 ms).
+    model = None
     spin_t0 = time.perf_counter()
     while not args.quick:
-        fit_resident()
+        model = fit_resident()
         torch.cuda.synchronize()
         go = torch.tensor([1 if time.perf_counter() - spin_t0 < SPINUP_S else 0], dtype=torch.int32, device=dev)
         if world > 1:
@@ -465,23 +484,29 @@ def run_b200(args, workload, data):
         if int(go.item()) == 0:
             break
     for _ in range(args.warmup):
-        fit_resident()
+        model = fit_resident()
+    # Python's cyclic collector stays ON, but what the process holds after warm-up (torch, scipy, numpy: ~10^6 tracked
+    # objects) is moved to the permanent generation: a full collection that walks all of it takes ~0.1 s and, landing
+    # inside a 0.22 s step, was the other source of single-step outliers (scripts/e2e_probe.py; timeit switches the
+    # collector off altogether for the same reason)
+    gc.collect()
+    gc.freeze()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = native.lib().mmu_launch_count()
     profiler.enable(1)            # coarse stages + the force kernel; the small kernels get their own pass below
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    model = None
     for _ in range(args.steps):
         model = fit_resident()
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = native.lib().mmu_launch_count() - launches0
-    stages = profiler.summarize(profiler.collect())
+    stage_rows = profiler.collect()
+    stages = profiler.summarize(stage_rows)
+    knn_each = [round(ms, 2) for (nm, ms, _) in stage_rows if nm == "knn"]      # per search call, in program order
     force_kernel = native.last_kernel("edge_forces")
     knn_kernel = native.last_kernel("knn_candidates")
     tail_kernel = native.last_kernel("epoch_tail")
@@ -504,12 +529,18 @@ def run_b200(args, workload, data):
 
     # end to end through the reference-facing API, host buffers in, host result out
     e2e_s = float("nan")
+    e2e_each = []
     if not args.quick:
-        fit_e2e()
+        for _ in range(max(1, args.warmup)):                # the same W warm-up steps as the device-timed loop
+            fit_e2e()
+        gc.collect()
+        gc.freeze()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             fit_e2e()
+            e2e_each.append(round(time.perf_counter() - t1, 4))
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop() if rank == 0 else None
@@ -655,11 +686,13 @@ def run_b200(args, workload, data):
                    "exchange": exchange, "knn_dist": knn_dist, "epoch_tail_kernel": tail_kernel or None,
                    "l2": "inputs (1.0 GB) exceed the 126 MB L2; every step re-reads them from HBM",
                    "spinup_s": 0.0 if args.quick else SPINUP_S,
+                   "python_gc": "enabled; gc.collect() + gc.freeze() after the warm-up steps",
                    "parallelism": f"kNN query-row blocks x{world}, optimiser edge shards x{world}" if world > 1 else "1 GPU"},
         "e2e": {"value": None if e2e_s != e2e_s else e2e_s, "unit": "s",
                 "h2d_bytes_per_step": h2d_total,
                 "h2d_bytes_per_rank": h2d_rank[0],
-                "d2h_bytes_per_step": int(sum(r * d * 4 for r in rows))},
+                "d2h_bytes_per_step": int(sum(r * d * 4 for r in rows)),
+                "seconds_each_step_rank0": e2e_each},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": dominant,
@@ -670,6 +703,7 @@ def run_b200(args, workload, data):
             "epoch_kernels_us_per_launch": {k: round(v["ms"] / max(v["calls"], 1) * 1e3, 1) for k, v in fine.items()
                                             if k in ("edge_sample", "edge_forces", "infonce", "adam", "epoch_tail")},
             "knn_tflops": knn_tflops,
+            "knn_ms_each_call": knn_each,
             "sgd_edge_updates_per_s": edge_updates * epochs / (opt_ms * 1e-3) if opt_ms else None,
             "sgd_gbs_whole_job": sgd_gbs_job,
             "sgd_gbs_per_gpu": sgd_gbs_job / world if sgd_gbs_job else None,
