@@ -205,3 +205,25 @@ def test_workload_table_matches_baseline_json(bench):
     assert (c2["k"], c2["out_dim"], c2["epochs"]) == (15, 16, 600)
     assert bench.OPT == dict(min_dist=0.1, num_rep=8, lr=0.01, alpha=1.0, batch_size=256)   # reference main.py:15-21
     assert "fit" in base["metric"].lower()
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_prints_the_contract_line_on_cpu():
+    """`bench.py --impl reference` (the arm the driver runs first on the GPU box) on the script's reduced self-test
+    workload: one JSON line with the engine arm's metric / unit / direction, `impl`, `cpu_baseline` and a zero-copy `e2e`;
+    no GPU involved (CUDA_VISIBLE_DEVICES is emptied by the script itself)."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2-tiny",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().split("\n") if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "umap_fit_seconds" and d["unit"] == "s"
+    assert d["higher_is_better"] is False and d["n_gpus"] == 1 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and abs(d["ms_per_step"] - 1e3 * d["value"]) < 1e-6 * d["ms_per_step"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "c2-tiny" and d["data"] == "synthetic"
