@@ -30,7 +30,6 @@ from __future__ import annotations
 import argparse
 import gc
 import json
-import math
 import os
 import statistics
 import subprocess

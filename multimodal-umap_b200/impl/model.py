@@ -19,7 +19,6 @@ from __future__ import annotations
 import functools
 import math
 import os
-import warnings
 import weakref
 
 import torch

@@ -95,7 +95,6 @@ def spectral_chebfsi_device(g: Graph, out_dim: int, tol: float = 3e-4, max_iter:
     One outer iteration = 1 SpMM (A x) + Gram (x^T A x) + 32x32 Jacobi + fused rotation of x and A x with the column
     residuals + the Ritz bookkeeping kernel + `degree` fused three-term SpMM steps + two SVQB orthonormalisations
     (Gram scaled to unit diagonal -> Jacobi -> T = D^-1 V Lambda^-1/2 -> rotation): ~27 launches of this library."""
-    import ctypes
     n, dev = g.n_rows, g.val.device
     m = out_dim + 1
     b = block_width(out_dim)
